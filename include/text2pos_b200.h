@@ -1,0 +1,206 @@
+/*
+ * text2pos_b200 -- C ABI of the B200-native Text2Pos hot path (sm_100a).
+ *
+ * The reference (mako443/Text2Pos-CVPR2022) is pure Python: it has no FFI layer.  Its only seam for
+ * this path is the nn.Module API (models/cell_retrieval.py:69-107, models/superglue_matcher.py:87-128,
+ * training/coarse.py:134-148).  Each entry point below replaces the library calls that one of those
+ * Python call sites makes today; the Python modules in text2pos_cvpr2022_b200/ (and the `models.*`
+ * shims) bind them with ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer;
+ *  - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise the
+ *    device, never free caller memory, hold no global mutable state (safe from several host threads on
+ *    distinct streams);
+ *  - return value: 0 = ok, <0 = error (T2P_ERR_*); t2p_last_error() gives a thread-local message;
+ *  - scratch memory is caller-provided: ask t2p_*_workspace() for the size;
+ *  - matrices are row-major, float32 unless stated; indices int32 unless stated.
+ */
+#ifndef TEXT2POS_B200_H
+#define TEXT2POS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2P_OK 0
+#define T2P_ERR_INVALID (-1)     /* bad argument */
+#define T2P_ERR_CUDA (-2)        /* CUDA runtime error */
+#define T2P_ERR_WORKSPACE (-3)   /* workspace too small */
+#define T2P_ERR_UNSUPPORTED (-4) /* shape outside the compiled range / not an sm_100 device */
+
+#define T2P_MAX_NEIGHBORS 32 /* torch_cluster radius() default max_num_neighbors (pointnet2.py:28-30) */
+#define T2P_KNN_K 8          /* DynamicEdgeConv k (cell_retrieval.py:46-48) */
+#define T2P_MAX_GNN_LAYERS 32
+
+typedef void* t2p_stream;
+
+int t2p_version(void);
+const char* t2p_last_error(void);
+/* sm count / compute capability of the current device; T2P_ERR_UNSUPPORTED unless cc 10.x */
+int t2p_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weights.  One immutable device copy of a packed float32 blob; the *_desc structs below address
+ * sub-arrays of it by offset (in floats).  Packing (BatchNorm folding, transposition to [K,N]) is done
+ * once by the host side from the reference's state_dict (text2pos_cvpr2022_b200/packing.py).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct t2p_weights t2p_weights;
+int t2p_weights_create(const float* h_blob, size_t n_floats, t2p_weights** out);
+int t2p_weights_destroy(t2p_weights* w);
+const float* t2p_weights_device_ptr(const t2p_weights* w);
+
+/* y = act(x . wT + bias): wT is [k, n] row-major at w_off, bias [n] at b_off (b_off < 0: no bias) */
+typedef struct {
+  int64_t w_off;
+  int64_t b_off;
+  int32_t k;
+  int32_t n;
+} t2p_linear_desc;
+
+/* ------------------------------------------------------------------------------------------------
+ * (a7) all-pairs scores + top-k.  Replaces training/coarse.py:134-148 (float64 numpy mat-vec + argsort).
+ * d_q [B,D], d_db [N,D] float32.  Output ordered by (score desc, index asc); scores are the float64
+ * dot products of the float32 inputs (the reference ranks in float64), indices are idx_base + row.
+ * If N < k the tail is filled with index -1 / score -inf.
+ * ------------------------------------------------------------------------------------------------ */
+size_t t2p_retrieve_topk_workspace(int B, int N, int D, int k);
+int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                      double* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes, t2p_stream stream);
+/* merge R per-shard lists [R,B,k_in] (e.g. after an all-gather) into [B,k_out], same ordering rule */
+int t2p_topk_merge(const double* d_scores, const int64_t* d_idx, int R, int B, int k_in, int k_out,
+                   double* d_out_scores, int64_t* d_out_idx, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a2) PointNet++ primitives, exposed for bit-exact index parity.
+ * Replaces torch_geometric fps()/radius() at models/pointcloud/pointnet2.py:26,28-30.
+ * d_pos [n_obj,P,3].  fps: start index 0, ties -> lowest index, m samples in selection order.
+ * ball query: for each centre the first `cap` (<=32) points of the same object in ascending index with
+ * d2 < r2 (strict); d_nbr [n_obj,m,cap] int32 padded with -1, d_count [n_obj,m].
+ * ------------------------------------------------------------------------------------------------ */
+int t2p_fps(const float* d_pos, int n_obj, int P, int m, int32_t* d_idx, t2p_stream stream);
+int t2p_ball_query(const float* d_pos, const int32_t* d_ctr_idx, int n_obj, int P, int m, float r2, int cap,
+                   int32_t* d_nbr, int32_t* d_count, t2p_stream stream);
+
+/* generic fused linear layer: y[M,n] (ld ldy) = act(x[M,k] (ld ldx) . wT + bias), relu in {0,1} */
+int t2p_linear(const t2p_weights* w, const t2p_linear_desc* lin, const float* d_x, int M, int ldx, int relu,
+               float* d_y, int ldy, t2p_stream stream);
+/* rows of x[M, width] (ld) scaled to unit L2 norm, eps 1e-12 (F.normalize) */
+int t2p_l2_normalize_rows(float* d_x, int M, int width, int ld, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a2,a3) PointNet2.forward(...).features2 for a batch of cells.
+ * Replaces models/pointcloud/pointnet2.py:80-100 as called per cell from models/object_encoder.py:92-95.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  t2p_linear_desc sa_l1[3]; /* BN-folded first local_nn layer, k = C_in + 3 (x rows first, then pos rows) */
+  t2p_linear_desc sa_l2[3]; /* BN-folded second local_nn layer */
+  float sa_radius_sq[3]; /* float32(float64(r)*float64(r)), r = 0.2/0.3/0.4 (pointnet2.py:57-59) */
+  t2p_linear_desc ga_l1, ga_l2; /* GlobalAbstraction mlp, k = 256 + 3 */
+  t2p_linear_desc lin1, lin2;
+  int32_t self_loop_quirk; /* PointConv(add_self_loops=True) flat-index self loops, see oracle/pointnet.py */
+} t2p_pointnet2_desc;
+
+size_t t2p_pointnet2_workspace(const t2p_pointnet2_desc* desc, int n_obj, int P);
+/* d_pos,d_rgb [n_obj,P,3]; d_obj_cell_start [n_obj]: index of the first object of the object's cell
+ * (only read when self_loop_quirk); d_features2 [n_obj,256].
+ * Optional debug outputs (may be NULL): d_dbg_idx[3] -> [n_obj,m_l] fps indices per layer,
+ * d_dbg_nbr[3] -> [n_obj,m_l,32] int32, d_dbg_cnt[3] -> [n_obj,m_l] int32, d_dbg_x[3] -> [n_obj,m_l,C_l]. */
+int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, const float* d_pos,
+                          const float* d_rgb, const int32_t* d_obj_cell_start, int n_obj, int P,
+                          float* d_features2, int32_t* const* d_dbg_idx, int32_t* const* d_dbg_nbr,
+                          int32_t* const* d_dbg_cnt, float* const* d_dbg_x, void* d_ws, size_t ws_bytes,
+                          t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a4) ObjectEncoder.forward tail: features2 (+ colour / centre) -> object embedding.
+ * Replaces models/object_encoder.py:98-138 (default flags).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  t2p_linear_desc mlp_pointnet;   /* 256 -> D */
+  t2p_linear_desc color_l1, color_l2; /* 3 -> 64 -> D */
+  t2p_linear_desc pos_l1, pos_l2;     /* 3 -> 64 -> D */
+  t2p_linear_desc merge;              /* 3D -> D, input order (class, color, position) */
+  int32_t embed_dim;
+} t2p_objenc_desc;
+
+size_t t2p_object_embed_workspace(const t2p_objenc_desc* desc, int n_obj);
+int t2p_object_embed(const t2p_weights* w, const t2p_objenc_desc* desc, const float* d_features2,
+                     const float* d_centers, const float* d_mean_rgb, int n_obj, float* d_emb, void* d_ws,
+                     size_t ws_bytes, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a5) CellRetrievalNetwork.encode_objects tail: normalise, DynamicEdgeConv(k=8,max), global max pool,
+ * lin, normalise.  Replaces models/cell_retrieval.py:94-105.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  t2p_linear_desc edge_ab; /* D -> 2D: [x_i.(W1a-W1b)+b1 | x_j.W1b] of graph1.nn layer 0 (BN folded) */
+  t2p_linear_desc edge_l2; /* D -> D graph1.nn layer 1 (BN folded) */
+  t2p_linear_desc lin_l1, lin_l2;
+  int32_t embed_dim;
+} t2p_cellagg_desc;
+
+size_t t2p_cell_aggregate_workspace(const t2p_cellagg_desc* desc, int n_obj, int n_cells);
+/* d_emb [n_obj,D] (un-normalised ObjectEncoder output), d_cell_offsets [n_cells+1] int32 (device),
+ * max_cell_objects = largest object count of any cell in the call (host knows it; <= 128),
+ * d_out [n_cells,D]; optional d_dbg_knn [n_obj,8] int32 (global object index or -1). */
+int t2p_cell_aggregate(const t2p_weights* w, const t2p_cellagg_desc* desc, const float* d_emb,
+                       const int32_t* d_cell_offsets, int n_obj, int n_cells, int max_cell_objects, float* d_out,
+                       int32_t* d_dbg_knn, void* d_ws, size_t ws_bytes, t2p_stream stream);
+/* the kNN of DynamicEdgeConv alone (bit-exact index parity): d_e [n_obj,D] -> d_knn [n_obj,8] */
+int t2p_knn_cells(const float* d_e, const int32_t* d_cell_offsets, int n_obj, int n_cells, int max_cell_objects,
+                  int D, int32_t* d_knn, int32_t* d_obj_cell, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a6) LanguageEncoder.forward (+ F.normalize of encode_text).
+ * Replaces models/modules.py:74-92: Embedding + packed 1-layer biLSTM + mean of the final states.
+ * The input projection is folded per vocabulary entry: xproj [2,V,4H] = emb . W_ih^T + b_ih + b_hh
+ * (gate order i,f,g,o); whh [2,H,4H] = W_hh^T per direction.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t xproj_off; /* [2, V, 4H] */
+  int64_t whh_off;   /* [2, H, 4H] */
+  int32_t vocab;     /* V (index 0 = <unk>/padding) */
+  int32_t hidden;    /* H */
+} t2p_lstm_desc;
+
+size_t t2p_lstm_encode_workspace(int B, int H);
+/* d_tokens [B,T] int32 (row b valid for t < d_lengths[b]), 1 <= lengths <= T.  d_out [B,H] =
+ * 0.5*(h_fwd_final + h_bwd_final), L2-normalised per row if normalize != 0. */
+int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32_t* d_tokens,
+                    const int32_t* d_lengths, int B, int T, int normalize, float* d_out, void* d_ws,
+                    size_t ws_bytes, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a8-a10) SuperGlue.forward: attentional GNN + final projection + log-space Sinkhorn + matching.
+ * Replaces models/superglue.py:239-330 (eval-mode BatchNorm folded into mlp0).
+ * Per layer (all [K,N] transposed): q,k,v,merge D->D, mlp0 2D->2D (BN folded), mlp3 2D->D.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  t2p_linear_desc q[T2P_MAX_GNN_LAYERS], k[T2P_MAX_GNN_LAYERS], v[T2P_MAX_GNN_LAYERS], merge[T2P_MAX_GNN_LAYERS];
+  t2p_linear_desc mlp0[T2P_MAX_GNN_LAYERS], mlp3[T2P_MAX_GNN_LAYERS];
+  int32_t is_cross[T2P_MAX_GNN_LAYERS];
+  t2p_linear_desc final_proj;
+  int32_t num_gnn_layers; /* len(GNN_layers) = 2 * args.num_layers */
+  int32_t dim;            /* D, divisible by 4 heads */
+  int32_t sinkhorn_iters;
+  float bin_score;
+  float match_threshold;
+} t2p_superglue_desc;
+
+size_t t2p_superglue_workspace(int B, int M, int N, int D);
+/* d_desc0 [B,M,D], d_desc1 [B,N,D] row layout (= reference desc.transpose(1,2)); outputs: d_P [B,M+1,N+1]
+ * (exp of the log assignment), d_matches0 [B,M] / d_matches1 [B,N] int64 (-1 = unmatched),
+ * d_mscores0 [B,M], d_mscores1 [B,N]; optional d_dbg_scores [B,M,N] (pre-Sinkhorn scores). */
+int t2p_superglue_forward(const t2p_weights* w, const t2p_superglue_desc* desc, const float* d_desc0,
+                          const float* d_desc1, int B, int M, int N, float* d_P, int64_t* d_matches0,
+                          int64_t* d_matches1, float* d_mscores0, float* d_mscores1, float* d_dbg_scores,
+                          void* d_ws, size_t ws_bytes, t2p_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXT2POS_B200_H */

@@ -1,0 +1,140 @@
+"""GPU: FPS / ball query (bit-exact) and the PointNet++ / object / cell encoders (fp32, <= 1e-4) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import cpu_state_dict
+from text2pos_cvpr2022_b200 import _lib, synthetic as syn
+from text2pos_cvpr2022_b200.object_encoder import obj_cell_start_from_offsets
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: "fp32 embeddings within 1e-4"
+
+
+def _fps_gpu(pos, m):
+    lib = _lib.load()
+    pos = pos.cuda().contiguous()
+    n, P, _ = pos.shape
+    idx = torch.empty(n, m, dtype=torch.int32, device="cuda")
+    _lib.check(lib.t2p_fps(_lib.ptr(pos), n, P, m, _lib.ptr(idx), _lib.stream_ptr()), "fps")
+    return idx
+
+
+def _ball_gpu(pos, idx, r):
+    lib = _lib.load()
+    pos = pos.cuda().contiguous()
+    n, P, _ = pos.shape
+    m = idx.shape[1]
+    nbr = torch.empty(n, m, 32, dtype=torch.int32, device="cuda")
+    cnt = torch.empty(n, m, dtype=torch.int32, device="cuda")
+    r2 = float(oracle.pointnet.radius_sq(r))
+    _lib.check(lib.t2p_ball_query(_lib.ptr(pos), _lib.ptr(idx.contiguous()), n, P, m, r2, 32, _lib.ptr(nbr), _lib.ptr(cnt),
+                                  _lib.stream_ptr()), "ball_query")
+    return nbr, cnt
+
+
+@pytest.mark.parametrize("P,m", [(256, 128), (128, 64), (64, 32), (100, 50), (8, 4), (33, 17), (1024, 512)])
+def test_fps_and_ball_query_bit_exact(P, m):
+    rng = np.random.default_rng(P)
+    objs = []
+    for o in range(24):
+        src = syn.synth_object(rng, n_src=[8, 40, 400, 2000][o % 4])
+        objs.append(syn.fixed_points_normalize(src.xyz, src.rgb, rng, P)[0])
+    pos = torch.from_numpy(np.stack(objs))
+    idx = _fps_gpu(pos, m)
+    ref = oracle.pointnet.fps(pos.numpy(), m)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref)
+    for r in (0.2, 0.4):
+        nbr, cnt = _ball_gpu(pos, idx, r)
+        cpos = np.take_along_axis(pos.numpy(), ref[:, :, None], axis=1)
+        rn, rc = oracle.pointnet.ball_query(pos.numpy(), cpos, r)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), rc)
+        np.testing.assert_array_equal(nbr.cpu().numpy(), rn)
+
+
+def test_fps_degenerate_duplicates():
+    pos = torch.zeros(3, 64, 3)
+    pos[1, 10:] = 0.5
+    assert _fps_gpu(pos, 8).cpu().tolist()[0] == [0] * 8
+    np.testing.assert_array_equal(_fps_gpu(pos, 8).cpu().numpy(), oracle.pointnet.fps(pos.numpy(), 8))
+
+
+@pytest.mark.parametrize("quirk", [True, False])
+def test_pointnet2_layers_match_oracle(coarse_model, quirk):
+    pn = coarse_model.object_encoder.pointnet
+    old = pn.self_loop_quirk
+    pn.self_loop_quirk = quirk
+    pn._t2p_invalidate()
+    try:
+        sd = cpu_state_dict(pn)
+        cells = syn.synth_packed_cells(11, 3)
+        dev = cells.to("cuda")
+        start = obj_cell_start_from_offsets(dev.cell_offsets)
+        f2, dbg = pn.features_packed(dev.pos, dev.rgb, start, debug=True)
+        ref = []
+        off = 0
+        for a, b in cells.cell_slices():
+            r, inter = oracle.pointnet.pointnet2_features(sd, "", cells.rgb[a:b], cells.pos[a:b], quirk, True)
+            ref.append(r)
+            for l in range(3):
+                st = inter[f"sa{l + 1}"]
+                np.testing.assert_array_equal(dbg["idx"][l][a:b].cpu().numpy(), st["idx"])  # bit-exact
+                np.testing.assert_array_equal(dbg["cnt"][l][a:b].cpu().numpy(), st["count"])
+                np.testing.assert_array_equal(dbg["nbr"][l][a:b].cpu().numpy(), st["nbr"])
+                np.testing.assert_allclose(dbg["x"][l][a:b].cpu().numpy(), st["x"].numpy(), atol=TOL, rtol=1e-4)
+        np.testing.assert_allclose(f2.cpu().numpy(), torch.cat(ref).numpy(), atol=TOL, rtol=1e-4)
+    finally:
+        pn.self_loop_quirk = old
+        pn._t2p_invalidate()
+
+
+def test_object_and_cell_encoder_match_oracle(coarse_model):
+    """Config 1: 128 synthetic cells through encode_objects (drop-in API) vs the oracle, <= 1e-4 abs."""
+    sd = cpu_state_dict(coarse_model)
+    cells_, objects, points = syn.synth_cells(0, 128)
+    packed = syn.pack_cells(objects, points)
+    out = coarse_model.encode_objects(objects, points)
+    assert out.shape == (128, 256) and out.is_cuda
+    sl = packed.cell_slices()
+    with torch.no_grad():
+        emb_ref = oracle.cells.object_encoder(sd, "object_encoder.", [packed.rgb[a:b] for a, b in sl],
+                                              [packed.pos[a:b] for a, b in sl], packed.centers, packed.mean_rgb)
+        ref = oracle.cells.cell_aggregate(sd, emb_ref, packed.cell_offsets.tolist())
+    emb = coarse_model.object_encoder.forward_packed(packed.to("cuda"))
+    np.testing.assert_allclose(emb.cpu().numpy(), emb_ref.numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=TOL, rtol=0)
+    assert (out >= 0).all() and torch.allclose(out.norm(dim=1), torch.ones(128, device="cuda"), atol=1e-5)
+
+
+def test_knn_bit_exact_and_small_cells(coarse_model):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    counts = [1, 2, 7, 8, 9, 16, 33]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    e = torch.nn.functional.normalize(torch.randn(int(off[-1]), 256, generator=g))
+    e[off[5] + 3] = e[off[5] + 1]  # duplicate embeddings inside a cell: distance ties
+    ed = e.cuda().contiguous()
+    knn = torch.empty(e.shape[0], 8, dtype=torch.int32, device="cuda")
+    oc = torch.empty(e.shape[0], dtype=torch.int32, device="cuda")
+    offd = torch.from_numpy(off).cuda()
+    _lib.check(lib.t2p_knn_cells(_lib.ptr(ed), _lib.ptr(offd), e.shape[0], len(counts), max(counts), 256, _lib.ptr(knn),
+                                 _lib.ptr(oc), _lib.stream_ptr()), "knn_cells")
+    got = knn.cpu().numpy()
+    for c, n in enumerate(counts):
+        ref = oracle.cells.knn_in_cell(e[off[c]:off[c + 1]].numpy()) + off[c]
+        np.testing.assert_array_equal(got[off[c]:off[c + 1], : ref.shape[1]], ref)
+        assert (got[off[c]:off[c + 1], ref.shape[1]:] == -1).all()
+        assert (oc[off[c]:off[c + 1]].cpu().numpy() == c).all()
+
+
+def test_cell_embedding_independent_of_batching(coarse_model):
+    """Property at any size: a cell's embedding does not depend on the other cells of the call."""
+    packed = syn.synth_packed_cells(21, 6).to("cuda")
+    full = coarse_model.encode_cells_packed(packed)
+    a, b = packed.cell_slices()[4]
+    one = syn.PackedCells(packed.pos[a:b], packed.rgb[a:b], packed.centers[a:b], packed.mean_rgb[a:b],
+                          torch.tensor([0, b - a], dtype=torch.int32))
+    single = coarse_model.encode_cells_packed(one)
+    assert torch.equal(full[4], single[0])

@@ -1,0 +1,124 @@
+"""CPU: host-side logic of the drop-in modules (tokeniser, packing/BN folding, cell packing, state_dict layout, loud failure)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import cpu_state_dict, load_golden
+from text2pos_cvpr2022_b200 import default_args, packing, synthetic as syn
+from text2pos_cvpr2022_b200.modules import LanguageEncoder, get_mlp, tokenize
+from text2pos_cvpr2022_b200.object_encoder import cell_chunks, obj_cell_start_from_offsets
+from text2pos_cvpr2022_b200.retrieval import shard_bounds
+from text2pos_cvpr2022_b200.runtime import AttrDict
+from text2pos_cvpr2022_b200.superglue import SuperGlue
+
+
+def _blob_linear(blob, d, x):
+    W = blob[d.w_off : d.w_off + d.k * d.n].reshape(d.k, d.n)
+    b = blob[d.b_off : d.b_off + d.n]
+    return x @ W + b
+
+
+def test_tokenizer_matches_oracle():
+    kw = {w: i + 1 for i, w in enumerate(syn.known_words())}
+    kw["<unk>"] = 0
+    texts = syn.synth_queries(3, 9) + ["The pose is, north. of a UNKNOWN thing"]
+    t0, l0 = oracle.text.tokenize(texts, kw)
+    t1, l1 = tokenize(texts, kw)
+    np.testing.assert_array_equal(t0, t1)
+    np.testing.assert_array_equal(l0, l1)
+    assert t1.dtype == np.int32 and 48 <= l1[0] <= 60
+
+
+def test_bn_folding_matches_oracle_get_mlp():
+    m = get_mlp([7, 12, 5])
+    syn.randomize_module_(m, 3)
+    sd = cpu_state_dict(m)
+    bb = packing.BlobBuilder()
+    d0 = packing.pack_mlp_layer(bb, sd, "0.")
+    d1 = packing.pack_mlp_layer(bb, sd, "1.")
+    blob = bb.finish().double().numpy()
+    x = torch.randn(11, 7, generator=torch.Generator().manual_seed(0))
+    h = np.maximum(_blob_linear(blob, d0, x.double().numpy()), 0)
+    y = np.maximum(_blob_linear(blob, d1, h), 0)
+    np.testing.assert_allclose(y, oracle.mlp.get_mlp(sd, "", x).numpy(), rtol=1e-5, atol=1e-6)
+    assert d0.w_off % 4 == 0 and d1.w_off % 4 == 0  # float4-aligned weight tiles
+
+
+def test_lstm_input_projection_folding():
+    enc = LanguageEncoder(syn.known_words(), 32, bi_dir=True)
+    syn.randomize_module_(enc, 4)
+    sd = cpu_state_dict(enc)
+    bb = packing.BlobBuilder()
+    d = packing.pack_lstm(bb, sd, "")
+    blob = bb.finish()
+    V, H = d.vocab, d.hidden
+    xproj = blob[d.xproj_off : d.xproj_off + 2 * V * 4 * H].reshape(2, V, 4 * H)
+    emb = sd["word_embedding.weight"]
+    ref = emb @ sd["lstm.weight_ih_l0_reverse"].t() + sd["lstm.bias_ih_l0_reverse"] + sd["lstm.bias_hh_l0_reverse"]
+    np.testing.assert_allclose(xproj[1].numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+    whh = blob[d.whh_off : d.whh_off + 2 * H * 4 * H].reshape(2, H, 4 * H)
+    np.testing.assert_array_equal(whh[0].numpy(), sd["lstm.weight_hh_l0"].t().numpy())
+
+
+def test_edgeconv_split_is_equivalent():
+    from text2pos_cvpr2022_b200.cell_retrieval import CellRetrievalNetwork
+
+    m = CellRetrievalNetwork(syn.KNOWN_CLASSES, syn.COLOR_NAMES, syn.known_words(), default_args(embed_dim=16))
+    syn.randomize_module_(m, 9)
+    sd = cpu_state_dict(m)
+    bb = packing.BlobBuilder()
+    d = packing.pack_cell_aggregation(bb, sd, 16)
+    blob = bb.finish().double().numpy()
+    g = torch.Generator().manual_seed(1)
+    xi, xj = torch.randn(5, 16, generator=g), torch.randn(5, 16, generator=g)
+    ab_i = _blob_linear(blob, d.edge_ab, xi.double().numpy())
+    ab_j = _blob_linear(blob, d.edge_ab, xj.double().numpy())
+    h1 = np.maximum(ab_i[:, :16] + ab_j[:, 16:], 0)
+    y = np.maximum(_blob_linear(blob, d.edge_l2, h1), 0)
+    ref = oracle.mlp.get_mlp(sd, "graph1.nn.", torch.cat([xi, xj - xi], dim=1))
+    np.testing.assert_allclose(y, ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_state_dict_layout_matches_reference_modules():
+    """Key names AND shapes equal those of the reference classes (recorded in the golden fixtures)."""
+    _, m = load_golden("superglue_fine.npz")
+    sg = SuperGlue({"descriptor_dim": m["D"], "GNN_layers": ["self", "cross"] * m["num_layers"], "sinkhorn_iterations": m["iters"]})
+    assert [(k, list(v.shape)) for k, v in sg.state_dict().items()] == [(k, list(s)) for k, s in m["spec"]]
+    _, m = load_golden("language_encoder_coarse.npz")
+    le = LanguageEncoder(m["words"], m["D"], bi_dir=True)
+    assert [(k, list(v.shape)) for k, v in le.state_dict().items()] == [(k, list(s)) for k, s in m["spec"]]
+
+
+def test_pack_cells_and_chunking():
+    cells, objects, points = syn.synth_cells(0, 5)
+    packed = syn.pack_cells(objects, points)
+    n = sum(len(o) for o in objects)
+    assert packed.pos.shape == (n, 256, 3) and packed.cell_offsets.tolist()[-1] == n
+    assert float(packed.pos.abs().max()) < 1.0
+    np.testing.assert_allclose(packed.centers[0].numpy(), objects[0][0].get_center(), rtol=1e-6)
+    start = obj_cell_start_from_offsets(packed.cell_offsets)
+    assert start.tolist() == [o for a, b in packed.cell_slices() for o in [a] * (b - a)]
+    off = [0, 5, 9, 20, 21]
+    assert cell_chunks(off, 10) == [(0, 2), (2, 3), (3, 4)]
+    assert cell_chunks(off, 1000) == [(0, 4)]
+    bad = syn.PointBatch(points[0].x[:-1], points[0].pos[:-1], points[0].batch[:-1])
+    with pytest.raises(ValueError):
+        syn.pack_cells(objects[:1], [bad])
+
+
+def test_shard_bounds():
+    assert shard_bounds(100000, 8) == [(i * 12500, (i + 1) * 12500) for i in range(8)]
+    assert shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def test_attrdict_and_loud_cpu_failure(coarse_model):
+    a = AttrDict()
+    a.P = 1
+    assert a["P"] == 1 and list(a) == ["P"] and "P" in a
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            coarse_model.encode_text(["The pose is north of a gray box."])
+        with pytest.raises(Exception):
+            coarse_model.forward()

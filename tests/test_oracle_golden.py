@@ -100,3 +100,15 @@ def test_retrieval_tie_rule():
     q = np.array([[1, 0, 0, 0]], dtype=np.float32)
     idx, _ = oracle.retrieval.topk(db, q, 5)
     assert idx.tolist() == [[1, 2, 4, 0, 5]]  # score desc, index asc
+
+
+def test_reference_port_language_encoder_matches_reference():
+    from oracle.reference_port import LanguageEncoderPort
+
+    for name in ("coarse", "fine"):
+        z, m = load_golden(f"language_encoder_{name}.npz")
+        sd = syn.synth_state_dict([(k, s) for k, s in m["spec"]], m["seed"])
+        kw = {w: i + 1 for i, w in enumerate(m["words"])}
+        kw["<unk>"] = 0
+        enc = LanguageEncoderPort(sd, "", kw)
+        np.testing.assert_allclose(enc(m["texts"]).numpy(), z["encodings"], rtol=1e-5, atol=1e-6)

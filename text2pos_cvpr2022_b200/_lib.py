@@ -1,0 +1,201 @@
+"""ctypes binding of the C ABI declared in ``include/text2pos_b200.h``.
+
+There is NO fallback: if ``lib/libtext2pos_b200.so`` is missing or a call fails, a
+``RuntimeError`` is raised.  Build the library with ``python -m text2pos_cvpr2022_b200.build``
+(or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libtext2pos_b200.so")
+
+MAX_NEIGHBORS = 32
+KNN_K = 8
+MAX_GNN_LAYERS = 32
+
+T2P_OK = 0
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [("w_off", C.c_int64), ("b_off", C.c_int64), ("k", C.c_int32), ("n", C.c_int32)]
+
+
+class PointNet2Desc(C.Structure):
+    _fields_ = [
+        ("sa_l1", LinearDesc * 3),
+        ("sa_l2", LinearDesc * 3),
+        ("sa_radius_sq", C.c_float * 3),
+        ("ga_l1", LinearDesc),
+        ("ga_l2", LinearDesc),
+        ("lin1", LinearDesc),
+        ("lin2", LinearDesc),
+        ("self_loop_quirk", C.c_int32),
+    ]
+
+
+class ObjEncDesc(C.Structure):
+    _fields_ = [
+        ("mlp_pointnet", LinearDesc),
+        ("color_l1", LinearDesc),
+        ("color_l2", LinearDesc),
+        ("pos_l1", LinearDesc),
+        ("pos_l2", LinearDesc),
+        ("merge", LinearDesc),
+        ("embed_dim", C.c_int32),
+    ]
+
+
+class CellAggDesc(C.Structure):
+    _fields_ = [
+        ("edge_ab", LinearDesc),
+        ("edge_l2", LinearDesc),
+        ("lin_l1", LinearDesc),
+        ("lin_l2", LinearDesc),
+        ("embed_dim", C.c_int32),
+    ]
+
+
+class LstmDesc(C.Structure):
+    _fields_ = [("xproj_off", C.c_int64), ("whh_off", C.c_int64), ("vocab", C.c_int32), ("hidden", C.c_int32)]
+
+
+class SuperGlueDesc(C.Structure):
+    _fields_ = [
+        ("q", LinearDesc * MAX_GNN_LAYERS),
+        ("k", LinearDesc * MAX_GNN_LAYERS),
+        ("v", LinearDesc * MAX_GNN_LAYERS),
+        ("merge", LinearDesc * MAX_GNN_LAYERS),
+        ("mlp0", LinearDesc * MAX_GNN_LAYERS),
+        ("mlp3", LinearDesc * MAX_GNN_LAYERS),
+        ("is_cross", C.c_int32 * MAX_GNN_LAYERS),
+        ("final_proj", LinearDesc),
+        ("num_gnn_layers", C.c_int32),
+        ("dim", C.c_int32),
+        ("sinkhorn_iters", C.c_int32),
+        ("bin_score", C.c_float),
+        ("match_threshold", C.c_float),
+    ]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_SZ = C.c_size_t
+
+# name -> (restype, argtypes).  Every symbol of include/text2pos_b200.h is listed (tests check the export list).
+PROTOTYPES = {
+    "t2p_version": (_I, []),
+    "t2p_last_error": (C.c_char_p, []),
+    "t2p_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "t2p_weights_create": (_I, [_P, _SZ, C.POINTER(_P)]),
+    "t2p_weights_destroy": (_I, [_P]),
+    "t2p_weights_device_ptr": (_P, [_P]),
+    "t2p_retrieve_topk_workspace": (_SZ, [_I, _I, _I, _I]),
+    "t2p_retrieve_topk": (_I, [_P, _P, _I, _I, _I, _I, C.c_int64, _P, _P, _P, _SZ, _P]),
+    "t2p_topk_merge": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "t2p_fps": (_I, [_P, _I, _I, _I, _P, _P]),
+    "t2p_ball_query": (_I, [_P, _P, _I, _I, _I, C.c_float, _I, _P, _P, _P]),
+    "t2p_linear": (_I, [_P, C.POINTER(LinearDesc), _P, _I, _I, _I, _P, _I, _P]),
+    "t2p_l2_normalize_rows": (_I, [_P, _I, _I, _I, _P]),
+    "t2p_knn_cells": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "t2p_pointnet2_workspace": (_SZ, [C.POINTER(PointNet2Desc), _I, _I]),
+    "t2p_pointnet2_forward": (
+        _I,
+        [_P, C.POINTER(PointNet2Desc), _P, _P, _P, _I, _I, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P],
+    ),
+    "t2p_object_embed_workspace": (_SZ, [C.POINTER(ObjEncDesc), _I]),
+    "t2p_object_embed": (_I, [_P, C.POINTER(ObjEncDesc), _P, _P, _P, _I, _P, _P, _SZ, _P]),
+    "t2p_cell_aggregate_workspace": (_SZ, [C.POINTER(CellAggDesc), _I, _I]),
+    "t2p_cell_aggregate": (_I, [_P, C.POINTER(CellAggDesc), _P, _P, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "t2p_lstm_encode_workspace": (_SZ, [_I, _I]),
+    "t2p_lstm_encode": (_I, [_P, C.POINTER(LstmDesc), _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
+    "t2p_superglue_workspace": (_SZ, [_I, _I, _I, _I]),
+    "t2p_superglue_forward": (
+        _I,
+        [_P, C.POINTER(SuperGlueDesc), _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    ),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed for loading)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"text2pos_b200: native library {LIB_PATH} is missing; build it with "
+                "`python -m text2pos_cvpr2022_b200.build` (there is no CPU / PyTorch fallback)"
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != T2P_OK:
+        msg = load().t2p_last_error()
+        raise RuntimeError(f"text2pos_b200 {what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int:
+    """Device (or host) pointer of a contiguous tensor; None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "text2pos_b200: tensors passed to the C ABI must be contiguous"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"text2pos_b200: {what} must live on a CUDA device (sm_100a); there is no CPU path")
+
+
+class Workspace:
+    """Grow-only scratch buffer per (device, stream-agnostic) owner."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        nbytes = max(int(nbytes), 256)
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class Weights:
+    """Owns a ``t2p_weights`` handle (an immutable device copy of a packed float32 blob)."""
+
+    def __init__(self, blob: torch.Tensor, device):
+        lib = load()
+        blob = blob.detach().to("cpu", torch.float32).contiguous()
+        self.n = blob.numel()
+        self.device = torch.device(device)
+        h = _P()
+        with torch.cuda.device(self.device):
+            check(lib.t2p_weights_create(blob.data_ptr(), self.n, C.byref(h)), "weights_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().t2p_weights_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -1,0 +1,38 @@
+// Internal host-side launchers shared between translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace t2p {
+
+// y[M,N] (ld ldy) = act(x[M,K] (ld ldx) . W[K,N] + bias)
+int launch_linear(const float* x, int M, int K, int ldx, const float* W, const float* bias, int N, bool relu,
+                  float* y, int ldy, cudaStream_t s);
+// y = act([xa | xb] . W + bias): xa [M,Ka] (ld lda), xb [M,Kb] (ld ldb), K = Ka + Kb
+int launch_linear_concat(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
+                         const float* bias, int N, bool relu, float* y, int ldy, cudaStream_t s);
+// out[row / rows_per_group, N] = max over the group's rows of relu([xa|xb] . W + bias); out must be zeroed
+int launch_linear_groupmax(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
+                           const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s);
+int launch_l2_normalize_rows(float* x, int M, int width, int ld, cudaStream_t s);
+
+// PointConv message + second local_nn layer + max aggregation for one set-abstraction level:
+//   out[o*m + c, :] = max over edges (j -> c) of relu(relu(T[j] - S[c]) . W2 + b2)
+// T [n_obj*P, C1] (first layer applied to [x_j | pos_j], bias included), S [n_obj*m, C1] (= pos_c . W1p).
+// Edges of centre c: its ball-query list (nbr/cnt) plus, with the quirk, flat point (lo*m + c) of the cell.
+int launch_sa_edge(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt,
+                   const int32_t* obj_cell_start, int quirk, int n_obj, int P, int m, int C1, const float* W2,
+                   const float* b2, int C2, float* out, cudaStream_t s);
+
+// DynamicEdgeConv second layer + max over neighbours + max over the cell's objects:
+//   pooled[cell(i), :] = max_i max_{j in knn(i)} relu(relu(AB[i, :D] + AB[j, D:]) . W2 + b2)
+int launch_edgeconv(const float* AB, const int32_t* knn, const int32_t* obj_cell, int n_obj, int D, const float* W2,
+                    const float* b2, float* pooled, cudaStream_t s);
+
+int launch_fps_ball(const float* pos, int n_obj, int P, int m, float r2, int32_t* ctr_idx, float* cpos,
+                    int32_t* nbr, int32_t* cnt, cudaStream_t s);
+int launch_fps_ball_mode(const float* pos, int n_obj, int P, int m, float r2, int mode, int do_ball, int32_t* ctr_idx,
+                         float* cpos, int32_t* nbr, int32_t* cnt, cudaStream_t s);
+int launch_knn_cells(const float* e, const int32_t* cell_offsets, int n_cells, int max_cell_objects, int D,
+                     int32_t* knn, int32_t* obj_cell, cudaStream_t s);
+
+}  // namespace t2p

@@ -1,0 +1,165 @@
+"""state_dict -> packed float32 blob + descriptor structs for the C ABI.
+
+All folding is done once, on the CPU, in float64 and rounded to float32 at the end:
+* eval-mode BatchNorm1d folded into the preceding Linear / Conv1d(k=1)
+  (``y = (xW^T + b - mean) * gamma / sqrt(var + eps) + beta``, eps = 1e-5);
+* weights transposed to ``[K, N]`` row-major so that kernel B-tile loads are coalesced;
+* LSTM input projection folded per vocabulary entry:
+  ``xproj[dir, v] = emb[v] @ W_ih^T + b_ih + b_hh`` (gate order i,f,g,o);
+* DynamicEdgeConv first layer split: ``W1 [x_i, x_j - x_i] = (W1a - W1b) x_i + W1b x_j``.
+
+The key layout is the reference's (SURVEY.md 8a "state_dict layout").
+"""
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5
+SA_RADII = (0.2, 0.3, 0.4)  # models/pointcloud/pointnet2.py:57-59 of the reference
+
+
+def _np64(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to("cpu", torch.float64).numpy()
+
+
+class BlobBuilder:
+    ALIGN = 64  # floats (256 bytes)
+
+    def __init__(self):
+        self.chunks = []
+        self.n = 0
+
+    def add(self, arr: np.ndarray) -> int:
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        off = self.n
+        pad = (-a.size) % self.ALIGN
+        self.chunks.append(a)
+        if pad:
+            self.chunks.append(np.zeros(pad))
+        self.n += a.size + pad
+        return off
+
+    def linear(self, W: np.ndarray, b: Optional[np.ndarray], bn: Optional[Dict[str, np.ndarray]] = None) -> _lib.LinearDesc:
+        """W [out, in] (nn.Linear layout), optional BN (dict weight,bias,running_mean,running_var)."""
+        W = np.asarray(W, dtype=np.float64)
+        out_f, in_f = W.shape
+        b = np.zeros(out_f) if b is None else np.asarray(b, dtype=np.float64)
+        if bn is not None:
+            s = bn["weight"] / np.sqrt(bn["running_var"] + BN_EPS)
+            W = W * s[:, None]
+            b = (b - bn["running_mean"]) * s + bn["bias"]
+        d = _lib.LinearDesc()
+        d.w_off = self.add(W.T)
+        d.b_off = self.add(b)
+        d.k, d.n = in_f, out_f
+        return d
+
+    def finish(self) -> torch.Tensor:
+        blob = np.concatenate(self.chunks) if self.chunks else np.zeros(1)
+        return torch.from_numpy(blob.astype(np.float32))
+
+
+def _bn(sd, prefix) -> Optional[Dict[str, np.ndarray]]:
+    if prefix + "running_mean" not in sd:
+        return None
+    return {k: _np64(sd[prefix + k]) for k in ("weight", "bias", "running_mean", "running_var")}
+
+
+def pack_mlp_layer(bb: BlobBuilder, sd, prefix: str) -> _lib.LinearDesc:
+    """One ``Sequential(Linear, [BatchNorm1d], ReLU)`` block of ``get_mlp`` stored under ``prefix`` (e.g. "lin.0.")."""
+    return bb.linear(_np64(sd[prefix + "0.weight"]), _np64(sd[prefix + "0.bias"]), _bn(sd, prefix + "1."))
+
+
+def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = True) -> _lib.PointNet2Desc:
+    d = _lib.PointNet2Desc()
+    for l in range(3):
+        p = f"{prefix}sa{l + 1}.point_conv.local_nn."
+        d.sa_l1[l] = pack_mlp_layer(bb, sd, p + "0.")
+        d.sa_l2[l] = pack_mlp_layer(bb, sd, p + "1.")
+        d.sa_radius_sq[l] = float(np.float32(float(SA_RADII[l]) * float(SA_RADII[l])))
+    d.ga_l1 = pack_mlp_layer(bb, sd, prefix + "ga.mlp.0.")
+    d.ga_l2 = pack_mlp_layer(bb, sd, prefix + "ga.mlp.1.")
+    d.lin1 = bb.linear(_np64(sd[prefix + "lin1.weight"]), _np64(sd[prefix + "lin1.bias"]))
+    d.lin2 = bb.linear(_np64(sd[prefix + "lin2.weight"]), _np64(sd[prefix + "lin2.bias"]))
+    d.self_loop_quirk = 1 if self_loop_quirk else 0
+    return d
+
+
+def pack_object_encoder(bb: BlobBuilder, sd, prefix: str, embed_dim: int) -> _lib.ObjEncDesc:
+    d = _lib.ObjEncDesc()
+    d.mlp_pointnet = pack_mlp_layer(bb, sd, prefix + "mlp_pointnet.0.")
+    d.color_l1 = pack_mlp_layer(bb, sd, prefix + "color_encoder.0.")
+    d.color_l2 = pack_mlp_layer(bb, sd, prefix + "color_encoder.1.")
+    d.pos_l1 = pack_mlp_layer(bb, sd, prefix + "pos_encoder.0.")
+    d.pos_l2 = pack_mlp_layer(bb, sd, prefix + "pos_encoder.1.")
+    d.merge = pack_mlp_layer(bb, sd, prefix + "mlp_merge.0.")
+    d.embed_dim = embed_dim
+    return d
+
+
+def pack_cell_aggregation(bb: BlobBuilder, sd, embed_dim: int) -> _lib.CellAggDesc:
+    D = embed_dim
+    d = _lib.CellAggDesc()
+    W1 = _np64(sd["graph1.nn.0.0.weight"])  # [D, 2D] acting on cat[x_i, x_j - x_i]
+    b1 = _np64(sd["graph1.nn.0.0.bias"])
+    bn = _bn(sd, "graph1.nn.0.1.")
+    if bn is not None:
+        s = bn["weight"] / np.sqrt(bn["running_var"] + BN_EPS)
+        W1 = W1 * s[:, None]
+        b1 = (b1 - bn["running_mean"]) * s + bn["bias"]
+    W1a, W1b = W1[:, :D], W1[:, D:]
+    Wab = np.concatenate([W1a - W1b, W1b], axis=0)  # [2D, D] "nn.Linear layout": rows = outputs [A | B]
+    d.edge_ab = bb.linear(Wab, np.concatenate([b1, np.zeros(D)]))
+    d.edge_l2 = pack_mlp_layer(bb, sd, "graph1.nn.1.")
+    d.lin_l1 = pack_mlp_layer(bb, sd, "lin.0.")
+    d.lin_l2 = pack_mlp_layer(bb, sd, "lin.1.")
+    d.embed_dim = D
+    return d
+
+
+def pack_lstm(bb: BlobBuilder, sd, prefix: str) -> _lib.LstmDesc:
+    emb = _np64(sd[prefix + "word_embedding.weight"])  # [V, D]
+    V, D = emb.shape
+    xproj, whh = [], []
+    for suffix in ("", "_reverse"):
+        w_ih = _np64(sd[f"{prefix}lstm.weight_ih_l0{suffix}"])  # [4H, D]
+        w_hh = _np64(sd[f"{prefix}lstm.weight_hh_l0{suffix}"])  # [4H, H]
+        b = _np64(sd[f"{prefix}lstm.bias_ih_l0{suffix}"]) + _np64(sd[f"{prefix}lstm.bias_hh_l0{suffix}"])
+        xproj.append(emb @ w_ih.T + b)  # [V, 4H]
+        whh.append(w_hh.T)  # [H, 4H]
+    H = whh[0].shape[0]
+    d = _lib.LstmDesc()
+    d.xproj_off = bb.add(np.stack(xproj))
+    d.whh_off = bb.add(np.stack(whh))
+    d.vocab, d.hidden = V, H
+    return d
+
+
+def pack_superglue(bb: BlobBuilder, sd, prefix: str, layer_names, sinkhorn_iters: int, match_threshold: float) -> _lib.SuperGlueDesc:
+    d = _lib.SuperGlueDesc()
+    n_layers = len(layer_names)
+    if n_layers > _lib.MAX_GNN_LAYERS:
+        raise ValueError(f"SuperGlue: {n_layers} GNN layers > {_lib.MAX_GNN_LAYERS}")
+
+    def conv(p, bn=None):
+        return bb.linear(_np64(sd[p + "weight"]).squeeze(-1), _np64(sd[p + "bias"]), bn)
+
+    for L, name in enumerate(layer_names):
+        p = f"{prefix}gnn.layers.{L}."
+        d.q[L] = conv(p + "attn.proj.0.")
+        d.k[L] = conv(p + "attn.proj.1.")
+        d.v[L] = conv(p + "attn.proj.2.")
+        d.merge[L] = conv(p + "attn.merge.")
+        d.mlp0[L] = conv(p + "mlp.0.", _bn(sd, p + "mlp.1."))
+        d.mlp3[L] = conv(p + "mlp.3.")
+        d.is_cross[L] = 1 if name == "cross" else 0
+    d.final_proj = conv(prefix + "final_proj.")
+    d.num_gnn_layers = n_layers
+    d.dim = int(sd[prefix + "final_proj.weight"].shape[0])
+    d.sinkhorn_iters = int(sinkhorn_iters)
+    d.bin_score = float(sd[prefix + "bin_score"])
+    d.match_threshold = float(match_threshold)
+    return d

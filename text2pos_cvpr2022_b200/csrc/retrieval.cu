@@ -20,7 +20,7 @@ retrieve_partial_kernel(const float* __restrict__ q, const float* __restrict__ d
                         int RG, int kp, float* __restrict__ part_s, int32_t* __restrict__ part_i) {
   extern __shared__ __align__(16) float rt_smem[];
   const int pass_rows = 4 * RG;
-  const int kc_pitch = min(D, RT_KC) + 4;
+  const int kc_pitch = ((min(D, RT_KC) + 3) & ~3) + 4;  // multiple of 4 floats: float4 rows stay 16-byte aligned
   float* Qs = rt_smem;                              // [RT_QT][kc_pitch]
   float* Ds = Qs + RT_QT * kc_pitch;                // [pass_rows][kc_pitch]
   float* St = Ds + pass_rows * kc_pitch;            // [RT_QT][pass_rows + 1]
@@ -266,9 +266,13 @@ static RetrievePlan make_plan(int B, int N, int D, int k, int sms) {
   p.rows_per_cta = (N + p.G - 1) / p.G;
   p.G = (N + p.rows_per_cta - 1) / p.rows_per_cta;
   int pass_rows = std::min(128, (p.rows_per_cta + 7) / 8 * 8);
+  const int kc_pitch = ((std::min(D, RT_KC) + 3) & ~3) + 4;
+  auto smem_of = [&](int pr) {
+    return ((size_t)(RT_QT + pr) * kc_pitch + (size_t)RT_QT * (pr + 1) + 2 * (size_t)RT_QT * RT_MAX_KP) * 4;
+  };
+  while (pass_rows > 8 && smem_of(pass_rows) > 220 * 1024) pass_rows -= 8;  // 227 KB per CTA on sm_100
   p.RG = pass_rows / 4;  // even -> blockDim multiple of 32
-  const int kc_pitch = std::min(D, RT_KC) + 4;
-  p.smem = ((size_t)(RT_QT + pass_rows) * kc_pitch + (size_t)RT_QT * (pass_rows + 1) + 2 * (size_t)RT_QT * RT_MAX_KP) * 4;
+  p.smem = smem_of(pass_rows);
   return p;
 }
 

@@ -3,11 +3,11 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1
-echo "== smoke" ; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -3 gpurun_out/smoke.log
-echo "== pytest gpu" ; timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -25 gpurun_out/pytest_gpu.log
-echo "== bench" ; timeout 600 python bench.py --steps 500 --warmup 20 > gpurun_out/bench.log 2> gpurun_out/bench.err ; echo "bench rc=$?" ; tail -2 gpurun_out/bench.log ; tail -5 gpurun_out/bench.err
+echo "== smoke" ; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -3 gpurun_out/smoke.log
+echo "== pytest gpu" ; timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -25 gpurun_out/pytest_gpu.log
+echo "== bench" ; timeout 400 python bench.py --steps 500 --warmup 20 > gpurun_out/bench.log 2> gpurun_out/bench.err ; echo "bench rc=$?" ; tail -2 gpurun_out/bench.log ; tail -5 gpurun_out/bench.err
 if [ "${1:-}" = "ncu" ]; then
   echo "== ncu launches"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+  timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
      python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
 fi

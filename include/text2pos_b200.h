@@ -158,13 +158,16 @@ int t2p_knn_cells(const float* d_e, const int32_t* d_cell_offsets, int n_obj, in
  * (a6) LanguageEncoder.forward (+ F.normalize of encode_text).
  * Replaces models/modules.py:74-92: Embedding + packed 1-layer biLSTM + mean of the final states.
  * The input projection is folded per vocabulary entry: xproj [2,V,4H] = emb . W_ih^T + b_ih + b_hh
- * (gate order i,f,g,o); whh [2,H,4H] = W_hh^T per direction.
+ * (gate order i,f,g,o); whh [2,H,4H] = W_hh^T per direction; whh_reg = the same matrix tiled per thread.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
-  int64_t xproj_off; /* [2, V, 4H] */
-  int64_t whh_off;   /* [2, H, 4H] */
-  int32_t vocab;     /* V (index 0 = <unk>/padding) */
-  int32_t hidden;    /* H */
+  int64_t xproj_off;   /* [2, V, 4H] */
+  int64_t whh_off;     /* [2, H, 4H] */
+  int64_t whh_reg_off; /* register-resident tiling of W_hh for H in {32,64,128,256} (csrc/lstm.cu), or -1:
+                          [2, H/32 (cluster rank r), H/32 (i), 4 (e), 256 (thread), 4 (gate g)] with
+                          thread = w*32 + kp*4 + jj  ->  W_hh[dir][g*H + 32 r + 4 w + jj][4*(8 i + kp) + e] */
+  int32_t vocab;       /* V (index 0 = <unk>/padding) */
+  int32_t hidden;      /* H */
 } t2p_lstm_desc;
 
 size_t t2p_lstm_encode_workspace(int B, int H);

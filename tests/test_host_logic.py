@@ -122,3 +122,18 @@ def test_attrdict_and_loud_cpu_failure(coarse_model):
             coarse_model.encode_text(["The pose is north of a gray box."])
         with pytest.raises(Exception):
             coarse_model.forward()
+
+
+def test_lstm_register_tiling_is_a_permutation_of_whh():
+    """packing._lstm_register_tiling: thread (w, kp, jj) of cluster rank r holds W_hh[g*H + 32r + 4w + jj][4*(8i+kp)+e]."""
+    from text2pos_cvpr2022_b200 import packing
+
+    rng = np.random.default_rng(0)
+    for H in (32, 64, 128, 256):
+        whh_t = rng.standard_normal((2, H, 4 * H))  # W_hh^T per direction
+        tiled = packing._lstm_register_tiling(whh_t)
+        assert tiled.shape == (2, H // 32, H // 32, 4, 256, 4)
+        assert np.array_equal(np.sort(tiled.reshape(2, -1), axis=1), np.sort(whh_t.reshape(2, -1), axis=1))
+        for (d, r, i, e, w, kp, jj, g) in [(0, 0, 0, 0, 0, 0, 0, 0), (1, H // 32 - 1, H // 32 - 1, 3, 7, 7, 3, 3), (1, 0, H // 64, 2, 5, 3, 1, 2)]:
+            t = w * 32 + kp * 4 + jj
+            assert tiled[d, r, i, e, t, g] == whh_t[d, 4 * (8 * i + kp) + e, g * H + 32 * r + 4 * w + jj]

@@ -60,7 +60,8 @@ class CellAggDesc(C.Structure):
 
 
 class LstmDesc(C.Structure):
-    _fields_ = [("xproj_off", C.c_int64), ("whh_off", C.c_int64), ("vocab", C.c_int32), ("hidden", C.c_int32)]
+    _fields_ = [("xproj_off", C.c_int64), ("whh_off", C.c_int64), ("whh_reg_off", C.c_int64), ("vocab", C.c_int32),
+                ("hidden", C.c_int32)]
 
 
 class SuperGlueDesc(C.Structure):

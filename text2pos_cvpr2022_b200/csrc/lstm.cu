@@ -175,6 +175,191 @@ lstm_finalize_kernel(const float* __restrict__ hfinal, int B, int H, int normali
   for (int c = lane; c < H; c += 32) out[(size_t)b * H + c] = 0.5f * (f[c] + r[c]) * inv;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Register-resident variant (H in {32,64,128,256}): the recurrent matrix never leaves the register file.
+//
+// Cluster of CS = H/32 CTAs per (direction, group of 8 sequences); CTA rank r owns hidden units
+// [32r, 32r+32) = 128 gate columns.  256 threads; thread (warp w, lane = kp*4 + jj) owns the 4 gates of unit
+// j = 4w + jj for the k values {4*(8i + kp) + e : i < H/32, e < 4} (H/8 of the H inputs), i.e. H/2 <= 128
+// weights in registers.  One step = H/8 broadcast float4 reads of h per sequence, 4*H FMAs per thread,
+// a 3-stage recursive-halving reduce-scatter over the 8 kp lanes (28 shuffles) that leaves lane kp with
+// the four complete gate pre-activations of sequence b = kp, the cell update in registers, a float4
+// gather over the 4 jj lanes and one 16-byte DSMEM store per peer CTA, then one cluster barrier.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int H>
+__global__ void __launch_bounds__(256, 1)
+lstm_reg_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_reg, const int32_t* __restrict__ tokens,
+                const int32_t* __restrict__ lengths, int B, int T, int V, float* __restrict__ hfinal) {
+  constexpr int CS = H / 32;  // CTAs per cluster
+  constexpr int NI = H / 32;  // float4 chunks of h per thread and sequence
+  extern __shared__ __align__(16) float lstm_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS;
+  const int dir = cid & 1, group = cid >> 1;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int kp = lane >> 2, jj = lane & 3;
+  const int u0 = rank * 32, j = 4 * w + jj;
+  const int b0 = group * LSTM_NB;
+
+  float* hbuf = lstm_smem;                                    // [2][NB][H]
+  int* tok = reinterpret_cast<int*>(hbuf + 2 * LSTM_NB * H);  // [NB][T]
+  int* len = tok + LSTM_NB * T;                               // [NB]
+
+  // register-resident weights: Wr[i][e] = the 4 gates (i,f,g,o) of unit j for k = 4*(8i + kp) + e
+  float4 Wr[NI][4];
+  {
+    const float4* src = reinterpret_cast<const float4*>(whh_reg) + ((size_t)(dir * CS + rank) * NI * 4) * 256 + tid;
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Wr[i][e] = __ldg(src + (size_t)(i * 4 + e) * 256);
+  }
+  for (int t = tid; t < 2 * LSTM_NB * H; t += 256) hbuf[t] = 0.f;
+  for (int t = tid; t < LSTM_NB * T; t += 256) {
+    const int b = t / T, tt = t - b * T;
+    const int v = (b0 + b < B) ? tokens[(size_t)(b0 + b) * T + tt] : 0;
+    tok[t] = (v < 0 || v >= V) ? 0 : v;
+  }
+  if (tid < LSTM_NB) len[tid] = (b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
+  __syncthreads();
+  int max_len = 0;
+#pragma unroll
+  for (int b = 0; b < LSTM_NB; ++b) max_len = max(max_len, len[b]);
+  const int my_len = len[kp];  // this lane finalises sequence b = kp
+  cluster_arrive_release();    // every CTA of the cluster is initialised before remote h writes start
+  cluster_wait_acquire();
+
+  const float* xp_base = xproj + (size_t)dir * V * 4 * H + u0 + j;
+  auto token_at = [&](int step) -> int {
+    if (step >= my_len) return 0;
+    return tok[kp * T + (dir ? (my_len - 1 - step) : step)];
+  };
+  float xn[4];
+  {
+    const float* xp = xp_base + (size_t)token_at(0) * 4 * H;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) xn[g] = __ldg(xp + g * H);
+  }
+  float c_state = 0.f, h_state = 0.f;
+
+  for (int step = 0; step < max_len; ++step) {
+    const float* hcur = hbuf + (size_t)(step & 1) * LSTM_NB * H + 4 * kp;
+    float* hnext = hbuf + (size_t)((step + 1) & 1) * LSTM_NB * H;
+    float xg[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) xg[g] = xn[g];
+    if (step + 1 < max_len) {  // next step's input projection: L2 latency hidden behind the FMAs below
+      const float* xp = xp_base + (size_t)token_at(step + 1) * 4 * H;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) xn[g] = __ldg(xp + g * H);
+    }
+    float acc[LSTM_NB][4];
+#pragma unroll
+    for (int b = 0; b < LSTM_NB; ++b)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[b][g] = 0.f;
+#pragma unroll
+    for (int b = 0; b < LSTM_NB; ++b) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 32 * i);
+        const float he[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[b][0] = fmaf(Wr[i][e].x, he[e], acc[b][0]);
+          acc[b][1] = fmaf(Wr[i][e].y, he[e], acc[b][1]);
+          acc[b][2] = fmaf(Wr[i][e].z, he[e], acc[b][2]);
+          acc[b][3] = fmaf(Wr[i][e].w, he[e], acc[b][3]);
+        }
+      }
+    }
+    // reduce-scatter over the 8 kp lanes: lane kp ends with the gates of sequence b = kp
+    float r1[4][4], r2[2][4], gate[4];
+    {
+      const bool up = (kp & 4) != 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float send = up ? acc[t][g] : acc[4 + t][g];
+          const float keep = up ? acc[4 + t][g] : acc[t][g];
+          r1[t][g] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+      const bool up = (kp & 2) != 0;
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float send = up ? r1[t][g] : r1[2 + t][g];
+          const float keep = up ? r1[2 + t][g] : r1[t][g];
+          r2[t][g] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+      const bool up = (kp & 1) != 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float send = up ? r2[0][g] : r2[1][g];
+        const float keep = up ? r2[1][g] : r2[0][g];
+        gate[g] = keep + __shfl_xor_sync(0xffffffffu, send, 4) + xg[g];
+      }
+    }
+    if (step < my_len) {
+      const float ig = sigmoidf_(gate[0]);
+      const float fg = sigmoidf_(gate[1]);
+      const float gg = tanhf(gate[2]);
+      const float og = sigmoidf_(gate[3]);
+      c_state = fmaf(fg, c_state, ig * gg);
+      h_state = og * tanhf(c_state);
+    }
+    // h_t[b = kp][u0 + 4w .. +3] gathered over the 4 jj lanes, then one float4 per peer CTA
+    float4 hv4;
+    hv4.x = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 0);
+    hv4.y = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 1);
+    hv4.z = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 2);
+    hv4.w = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 3);
+    float* dst_local = hnext + kp * H + u0 + 4 * w;
+#pragma unroll
+    for (int r = jj; r < CS; r += 4) {
+      float* remote = cluster.map_shared_rank(dst_local, r);
+      *reinterpret_cast<float4*>(remote) = hv4;
+    }
+    cluster_arrive_release();  // h_t complete in every CTA; also orders this step's reads before the next overwrite
+    cluster_wait_acquire();
+  }
+  if (b0 + kp < B) hfinal[((size_t)dir * B + b0 + kp) * H + u0 + j] = h_state;
+}
+
+template <int H>
+static int lstm_reg_launch(const float* xproj, const float* whh_reg, const int32_t* tokens, const int32_t* lengths, int B,
+                           int T, int V, float* hfinal, cudaStream_t s) {
+  auto kern = lstm_reg_kernel<H>;
+  const size_t smem = (size_t)2 * LSTM_NB * H * sizeof(float) + ((size_t)LSTM_NB * T + LSTM_NB) * sizeof(int);
+  T2P_REQUIRE(smem <= 200 * 1024, T2P_ERR_UNSUPPORTED, "lstm_encode: T=%d needs %zu bytes of shared memory", T, smem);
+  if (smem > 48 * 1024) T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int groups = (B + LSTM_NB - 1) / LSTM_NB;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * 2 * (H / 32));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = H / 32;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  T2P_CUDA(cudaLaunchKernelEx(&cfg, kern, xproj, whh_reg, tokens, lengths, B, T, V, hfinal));
+  return T2P_OK;
+}
+
 struct LstmPlan {
   int CS, HU, RPT;
   size_t smem;
@@ -244,14 +429,29 @@ int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32
                   (size_t)desc->xproj_off + (size_t)2 * V * 4 * H <= w->n_floats &&
                   (size_t)desc->whh_off + (size_t)2 * H * 4 * H <= w->n_floats,
               T2P_ERR_INVALID, "lstm_encode: descriptor outside the weight blob");
+  cudaStream_t s = as_stream(stream);
+  const float* xproj = wptr(w, desc->xproj_off);
+  if (desc->whh_reg_off >= 0 && (H == 32 || H == 64 || H == 128 || H == 256)) {
+    T2P_REQUIRE((size_t)desc->whh_reg_off + (size_t)2 * H * 4 * H <= w->n_floats, T2P_ERR_INVALID,
+                "lstm_encode: whh_reg outside the weight blob");
+    Arena a(d_ws, ws_bytes);
+    float* hfinal = a.take<float>((size_t)2 * B * H);
+    T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "lstm_encode: workspace %zu < %zu bytes", ws_bytes, a.used);
+    const float* wr = wptr(w, desc->whh_reg_off);
+    if (H == 256) T2P_TRY(lstm_reg_launch<256>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else if (H == 128) T2P_TRY(lstm_reg_launch<128>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else if (H == 64) T2P_TRY(lstm_reg_launch<64>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else T2P_TRY(lstm_reg_launch<32>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    lstm_finalize_kernel<<<(B + 7) / 8, 256, 0, s>>>(hfinal, B, H, normalize, d_out);
+    T2P_LAUNCH_CHECK();
+    return T2P_OK;
+  }
   const LstmPlan p = lstm_plan(H, T);
   T2P_REQUIRE(p.ok, T2P_ERR_UNSUPPORTED,
               "lstm_encode: hidden=%d not supported (need H = CS*HU with CS in {1,2,4,8}, HU in {16,32,64})", H);
   Arena a(d_ws, ws_bytes);
   float* hfinal = a.take<float>((size_t)2 * B * H);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "lstm_encode: workspace %zu < %zu bytes", ws_bytes, a.used);
-  cudaStream_t s = as_stream(stream);
-  const float* xproj = wptr(w, desc->xproj_off);
   const float* whh = wptr(w, desc->whh_off);
   if (p.RPT == 8) T2P_TRY(lstm_launch<8>(p, xproj, whh, d_tokens, d_lengths, B, T, H, V, hfinal, s));
   else if (p.RPT == 4) T2P_TRY(lstm_launch<4>(p, xproj, whh, d_tokens, d_lengths, B, T, H, V, hfinal, s));

@@ -1,0 +1,557 @@
+// (a7) all-pairs scores + top-k on the tcgen05 tensor cores: TMA-fed TF32 scan with an in-kernel top-k,
+// followed by a certified exact (float64) re-rank.
+//
+//   scan   (retrieve_scan_tc_kernel): persistent CTAs, one per SM.  The query tile [128 x D] stays resident in
+//           shared memory (TMA, 128-byte swizzle); DB row tiles [tile_n x 32 floats] stream through a 4-stage
+//           TMA/mbarrier ring; one elected thread issues tcgen05.mma kind::tf32 (M = 128 queries, N = tile_n
+//           rows, K = 8 per instruction) into a double-buffered TMEM accumulator; four epilogue warps read their
+//           TMEM lane quadrant (lane = query) with tcgen05.ld and keep, per query, the KP best rows of the CTA as
+//           sorted 32-bit keys in registers (score bits with the low bits replaced by the local row index --
+//           min/max insertion, no divergence).
+//   select (retrieve_select_kernel): one CTA per query.  Radix-selects the NC best keys over all CTAs,
+//           re-scores those candidates in float64 (the reference ranks float64 dot products of the float32
+//           embeddings, training/coarse.py:100-103,136), orders them by (score desc, index asc) and CERTIFIES
+//           the result: every row that is not a candidate has a TF32 score <= U, hence a true score
+//           <= U + eps*|q|*max|d|; if the k-th exact score is not above that bound the CTA falls back to an exact
+//           float64 scan of the whole DB for its query.  The output therefore always equals the float64 ranking;
+//           TF32 only decides how fast it is obtained.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "kernels.h"
+#include "sm100.cuh"
+#include "topk.cuh"
+
+namespace t2p {
+
+using namespace sm100;
+
+constexpr int TC_QM = 128;          // queries per tile (UMMA M)
+constexpr int TC_TILE_MAX = 128;    // DB rows per tile (UMMA N), multiple of 16
+constexpr int TC_STAGES = 4;
+constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 32 floats
+constexpr int TC_THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int TC_MAX_TILES_PER_CTA = 16;
+constexpr int TC_TMEM_COLS = 256;   // 2 accumulators x 128 columns
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_CAND_MAX = 64;
+// |tf32 score - exact score| <= TC_EPS * |q| * |d|: both operands lose < 2^-10 relative (13 mantissa bits dropped),
+// plus the fp32 accumulation of <= 256 products inside the tensor core.
+constexpr double TC_EPS = 2.2e-3;
+
+// ---- order-preserving 32-bit keys ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t score_to_key(float s, uint32_t low_mask, uint32_t local) {
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (u & ~low_mask) | (low_mask - local);  // lower local index wins among equal (truncated) scores
+}
+// largest score whose key could be `key`
+__device__ __forceinline__ float key_upper_score(uint32_t key, uint32_t low_mask) {
+  uint32_t u = key | low_mask;
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+// ---- max squared row norm of the DB (input of the certification bound) -------------------------------------
+__global__ void __launch_bounds__(256) row_norm2_max_kernel(const float* __restrict__ db, int N, int D, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float best = 0.f;
+  for (int r = warp; r < N; r += nwarps) {
+    const float* p = db + (size_t)r * D;
+    float ss = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float v = __ldg(p + c);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    best = fmaxf(best, ss);
+  }
+  if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));
+}
+
+// ---- scan ----------------------------------------------------------------------------------------------
+struct ScanSmem {
+  uint64_t q_full;
+  uint64_t full[TC_STAGES];
+  uint64_t empty[TC_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_slot;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db, int B, int N,
+                        int D, int tile_n, int q_box_rows, int db_box_rows, int nb_bits, uint32_t* __restrict__ part_keys) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nch = D >> 5;  // 128-byte chunks along K
+  uint8_t* q_smem = base;
+  uint8_t* st_smem = base + (size_t)nch * TC_CHUNK_BYTES;
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(st_smem + (size_t)TC_STAGES * TC_CHUNK_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int q0 = blockIdx.y * TC_QM;
+  const int tiles = (N + tile_n - 1) / tile_n;
+  const int my_tiles = (tiles - c + G - 1) / G;  // host guarantees c < tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm->q_full, 1);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&sm->full[s], 1);
+      mbar_init(&sm->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sm->tmem_full[a], 1);
+      mbar_init(&sm->tmem_empty[a], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(&sm->tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = sm->tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_db);
+      mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_box_rows * 128));
+      for (int kc = 0; kc < nch; ++kc) tma_load_2d(q_smem + (size_t)kc * TC_CHUNK_BYTES, &tmap_q, kc * 32, q0, &sm->q_full);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int row0 = (c + lt * G) * tile_n;
+        for (int kc = 0; kc < nch; ++kc) {
+          mbar_wait(&sm->empty[stage], ph ^ 1);
+          mbar_expect_tx(&sm->full[stage], (uint32_t)(db_box_rows * 128));
+          tma_load_2d(st_smem + (size_t)stage * TC_CHUNK_BYTES, &tmap_db, kc * 32, row0, &sm->full[stage]);
+          if (++stage == TC_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TC_QM, tile_n);
+      const uint32_t q_addr = smem_u32(q_smem), st_addr = smem_u32(st_smem);
+      mbar_wait(&sm->q_full, 0);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&sm->tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * TC_TILE_MAX;
+        for (int kc = 0; kc < nch; ++kc) {
+          mbar_wait(&sm->full[stage], ph);
+          tc_fence_after_sync();
+          const uint64_t a_desc = umma_desc_sw128_kmajor(q_addr + kc * TC_CHUNK_BYTES);
+          const uint64_t b_desc = umma_desc_sw128_kmajor(st_addr + stage * TC_CHUNK_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
+            umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+          umma_commit(&sm->empty[stage]);
+          if (++stage == TC_STAGES) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(&sm->tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM lane = query, columns = DB rows of the tile =====
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+    const int qrow = q0 + quad * 32 + lane;
+    const bool warp_active = (q0 + quad * 32) < B;
+    const uint32_t low_mask = (1u << nb_bits) - 1u;
+    uint32_t L[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) L[i] = 0u;
+    const int nchunks = (tile_n + 31) >> 5;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(&sm->tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after_sync();
+      if (warp_active) {
+        const int row0 = (c + lt * G) * tile_n;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_TILE_MAX + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = ch * 32 + j;
+            const bool ok = (col < tile_n) && (row0 + col < N);
+            uint32_t x = ok ? score_to_key(__uint_as_float(v[j]), low_mask, (uint32_t)(lt * TC_TILE_MAX + col)) : 0u;
+            if (__any_sync(0xffffffffu, x > L[KP - 1])) {
+#pragma unroll
+              for (int i = 0; i < KP; ++i) {
+                const uint32_t hi = max(L[i], x);
+                x = min(L[i], x);
+                L[i] = hi;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&sm->tmem_empty[acc]);
+    }
+    if (qrow < B) {
+      uint4* dst = reinterpret_cast<uint4*>(part_keys + ((size_t)qrow * G + c) * KP);
+#pragma unroll
+      for (int i = 0; i < KP / 4; ++i) dst[i] = make_uint4(L[4 * i], L[4 * i + 1], L[4 * i + 2], L[4 * i + 3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+}
+
+// ---- select ----------------------------------------------------------------------------------------------
+// float64 dot product of one query and one DB row by one warp (lanes stride the channels, fixed xor tree)
+__device__ __forceinline__ double warp_dot_f64(const float* __restrict__ q_smem, const float* __restrict__ d, int D, int lane) {
+  double acc = 0.0;
+  for (int ch = lane; ch < D; ch += 32) acc = fma((double)q_smem[ch], (double)__ldg(d + ch), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+struct SelSmem {
+  unsigned hist[256];
+  unsigned sel_prefix, sel_remaining, n_cand, below_max, m_last, fallback;
+  uint32_t cand_key[SEL_CAND_MAX];
+  int32_t cand_row[SEL_CAND_MAX];
+  double cand_score[SEL_CAND_MAX];
+  double wl_s[8][32];
+  int64_t wl_i[8][32];
+};
+
+__global__ void __launch_bounds__(SEL_THREADS)
+retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, int B, int N, int D, int G, int KP, int NC, int k,
+                       int tile_n, int nb_bits, int64_t idx_base, const uint32_t* __restrict__ part_keys,
+                       const float* __restrict__ db_norm2_max, int force_rescan, double* __restrict__ out_s,
+                       int64_t* __restrict__ out_i, int32_t* __restrict__ stats) {
+  extern __shared__ __align__(16) uint8_t sel_raw[];
+  SelSmem* sm = reinterpret_cast<SelSmem*>(sel_raw);
+  float* qs = reinterpret_cast<float*>(sel_raw + sizeof(SelSmem));  // [D]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(qs + D);               // [G*KP]
+  const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = G * KP;
+  const uint32_t low_mask = (1u << nb_bits) - 1u;
+  const double NINF = __longlong_as_double(0xfff0000000000000LL);
+
+  for (int t = tid; t < D; t += SEL_THREADS) qs[t] = __ldg(q + (size_t)qi * D + t);
+  {
+    const uint32_t* src = part_keys + (size_t)qi * total;
+    for (int t = tid; t < total; t += SEL_THREADS) keys[t] = src[t];
+  }
+  if (tid == 0) {
+    sm->sel_prefix = 0;
+    sm->sel_remaining = (unsigned)NC;
+    sm->n_cand = 0;
+    sm->below_max = 0;
+    sm->m_last = 0;
+    sm->fallback = 0;
+  }
+  __syncthreads();
+
+  // radix select (4 x 8 bits, most significant first): tau = NC-th largest key
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    sm->hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = sm->sel_prefix;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int t = tid; t < total; t += SEL_THREADS) {
+      const uint32_t x = keys[t];
+      if ((x & himask) == prefix) atomicAdd(&sm->hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {  // bins from the top: find the bin in which the running count reaches `remaining`
+      unsigned mine = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) mine += sm->hist[255 - (lane * 8 + b)];
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned remaining = sm->sel_remaining;
+      const unsigned before = incl - mine;
+      const bool here = (before < remaining) && (incl >= remaining);
+      const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot < remaining) {
+        if (lane == 0) {  // fewer keys than NC in this subtree: everything qualifies, tau = smallest
+          sm->sel_remaining = 0;
+          sm->sel_prefix = prefix;  // low bits zero -> all keys with this prefix are >= tau
+        }
+      } else if (here) {
+        unsigned run = before;
+        for (int b = 0; b < 8; ++b) {
+          const int bin = 255 - (lane * 8 + b);
+          const unsigned h = sm->hist[bin];
+          if (run + h >= remaining) {
+            sm->sel_prefix = prefix | ((unsigned)bin << shift);
+            sm->sel_remaining = remaining - run;
+            break;
+          }
+          run += h;
+        }
+      }
+    }
+    __syncthreads();
+    if (sm->sel_remaining == 0) break;
+  }
+  const uint32_t tau = sm->sel_prefix;
+  __syncthreads();
+
+  // candidates: keys >= tau (non-empty); bounds for the certification: largest key < tau, largest "last slot" key
+  for (int t = tid; t < total; t += SEL_THREADS) {
+    const uint32_t x = keys[t];
+    if (x != 0u && x >= tau) {
+      const unsigned slot = atomicAdd(&sm->n_cand, 1u);
+      if (slot < SEL_CAND_MAX) {
+        const int cta = t / KP;
+        const uint32_t local = low_mask - (x & low_mask);
+        sm->cand_key[slot] = x;
+        sm->cand_row[slot] = (cta + (int)(local >> 7) * G) * tile_n + (int)(local & 127u);
+      }
+    } else if (x != 0u) {
+      atomicMax(&sm->below_max, x);
+    }
+    if ((t % KP) == KP - 1) atomicMax(&sm->m_last, x);  // a full list may hide rows up to its last key
+  }
+  __syncthreads();
+  const int n_cand = (int)sm->n_cand;
+  bool need_rescan = force_rescan != 0 || n_cand > SEL_CAND_MAX;
+
+  if (!need_rescan) {
+    for (int f = warp; f < n_cand; f += SEL_THREADS / 32) {
+      const double s = warp_dot_f64(qs, db + (size_t)sm->cand_row[f] * D, D, lane);
+      if (lane == 0) sm->cand_score[f] = s;
+    }
+    __syncthreads();
+    // rank by (score desc, row asc); k-th best exact score
+    int my_rank = -1;
+    if (tid < n_cand) {
+      const double ms = sm->cand_score[tid];
+      const int mr = sm->cand_row[tid];
+      int r = 0;
+      for (int g = 0; g < n_cand; ++g) {
+        const double gs = sm->cand_score[g];
+        const int gr = sm->cand_row[g];
+        r += (gs > ms || (gs == ms && gr < mr)) ? 1 : 0;
+      }
+      my_rank = r;
+    }
+    // certification
+    if (warp == 0) {
+      double qq = 0.0;
+      for (int ch = lane; ch < D; ch += 32) qq = fma((double)qs[ch], (double)qs[ch], qq);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+      if (lane == 0) {
+        const uint32_t ukey = max(sm->below_max, sm->m_last);
+        bool certified = true;
+        if (ukey != 0u) {
+          if (n_cand < k) {
+            certified = false;
+          } else {
+            double tk = NINF;  // k-th best exact score
+            // (computed below by the thread holding rank k-1; here recompute cheaply)
+            for (int g = 0; g < n_cand; ++g) {
+              int r = 0;
+              const double ms = sm->cand_score[g];
+              const int mr = sm->cand_row[g];
+              for (int h = 0; h < n_cand; ++h) {
+                const double gs = sm->cand_score[h];
+                const int gr = sm->cand_row[h];
+                r += (gs > ms || (gs == ms && gr < mr)) ? 1 : 0;
+              }
+              if (r == k - 1) tk = ms;
+            }
+            const double bound = (double)key_upper_score(ukey, low_mask) +
+                                 TC_EPS * sqrt(qq) * sqrt((double)__ldg(db_norm2_max) * (1.0 + 1e-5));
+            certified = tk > bound;
+          }
+        }
+        sm->fallback = certified ? 0u : 1u;
+      }
+    }
+    __syncthreads();
+    need_rescan = sm->fallback != 0u;
+    if (!need_rescan) {
+      if (tid < n_cand && my_rank < k) {
+        out_s[(size_t)qi * k + my_rank] = sm->cand_score[tid];
+        out_i[(size_t)qi * k + my_rank] = idx_base + (int64_t)sm->cand_row[tid];
+      }
+      for (int r = n_cand + tid; r < k; r += SEL_THREADS) {  // N < k: pad
+        out_s[(size_t)qi * k + r] = NINF;
+        out_i[(size_t)qi * k + r] = -1;
+      }
+      if (tid == 0 && stats) atomicAdd(stats + 0, 1);
+      return;
+    }
+  }
+
+  // exact float64 rescan of the whole DB for this query (rare: dense ties / clustered scores / forced)
+  {
+    const int64_t IMAX = 0x7fffffffffffffffLL;
+    WarpTopK<double, int64_t> top;
+    top.init(k, NINF, IMAX);
+    for (int r0 = warp * 32; r0 < N; r0 += SEL_THREADS) {  // each warp: 32 consecutive rows per round, lane l keeps row r0+l
+      double mine = NINF;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r = r0 + rr;
+        if (r < N) {  // warp-uniform
+          const double s = warp_dot_f64(qs, db + (size_t)r * D, D, lane);
+          if (lane == rr) mine = s;
+        }
+      }
+      top.offer(r0 + lane < N, mine, (int64_t)(r0 + lane));
+    }
+    sm->wl_s[warp][lane] = top.s;
+    sm->wl_i[warp][lane] = top.i;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < SEL_THREADS / 32; ++w) top.offer(lane < k && sm->wl_i[w][lane] != IMAX, sm->wl_s[w][lane], sm->wl_i[w][lane]);
+      if (lane < k) {
+        const bool ok = top.i != IMAX;
+        out_s[(size_t)qi * k + lane] = ok ? top.s : NINF;
+        out_i[(size_t)qi * k + lane] = ok ? idx_base + top.i : (int64_t)-1;
+      }
+      if (lane == 0 && stats) atomicAdd(stats + 1, 1);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// [rows, D] float32 row-major, box = [box_rows x 32 floats], 128-byte swizzle, out-of-bounds rows read as zero
+static int make_tmap_rows(CUtensorMap* m, const float* ptr, int rows, int D, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  T2P_REQUIRE(fn != nullptr, T2P_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  T2P_REQUIRE(r == CUDA_SUCCESS, T2P_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d D=%d box_rows=%d)", (int)r,
+              rows, D, box_rows);
+  return T2P_OK;
+}
+
+struct TcPlan {
+  bool ok;
+  int KP, NC, tile_n, tiles, G, tiles_per_cta, nb_bits, qtiles;
+  size_t scan_smem, sel_smem;
+};
+
+static int ceil_log2(int x) {
+  int b = 0;
+  while ((1 << b) < x) ++b;
+  return b;
+}
+
+TcPlan tc_plan(int B, int N, int D, int k, int sms) {
+  TcPlan p = {};
+  p.ok = false;
+  if (D % 32 != 0 || D < 32 || D > 256 || k < 1 || k > 26 || N < 1 || B < 1) return p;
+  if ((reinterpret_cast<uintptr_t>(nullptr)) != 0) return p;
+  p.KP = k <= 16 ? 16 : 32;
+  p.NC = k <= 16 ? 32 : 48;
+  p.qtiles = (B + TC_QM - 1) / TC_QM;
+  // rows per tile: spread the DB over all SMs when it is small, 128-row tiles otherwise
+  int per_sm = (N + sms - 1) / sms;
+  p.tile_n = std::min(TC_TILE_MAX, std::max(16, (per_sm + 15) / 16 * 16));
+  p.tiles = (N + p.tile_n - 1) / p.tile_n;
+  p.G = std::min(p.tiles, sms);
+  p.tiles_per_cta = (p.tiles + p.G - 1) / p.G;
+  if (p.tiles_per_cta > TC_MAX_TILES_PER_CTA) {  // keep the index field of the keys small: more CTAs than SMs
+    p.tiles_per_cta = TC_MAX_TILES_PER_CTA;
+    p.G = (p.tiles + TC_MAX_TILES_PER_CTA - 1) / TC_MAX_TILES_PER_CTA;
+  }
+  p.nb_bits = 7 + ceil_log2(p.tiles_per_cta);
+  p.scan_smem = 1024 + (size_t)(D / 32 + TC_STAGES) * TC_CHUNK_BYTES + sizeof(ScanSmem) + 64;
+  p.sel_smem = sizeof(SelSmem) + (size_t)D * 4 + (size_t)p.G * p.KP * 4;
+  if (p.scan_smem > 227 * 1024 || p.sel_smem > 200 * 1024) return p;
+  p.ok = true;
+  return p;
+}
+
+size_t tc_workspace_bytes(const TcPlan& p, int B) {
+  return align_up((size_t)B * p.G * p.KP * sizeof(uint32_t), 256) + 256 /* norm bound */;
+}
+
+int launch_row_norm2_max(const float* db, int N, int D, float* out, cudaStream_t s) {
+  T2P_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  const int blocks = std::max(1, std::min(592, (N + 7) / 8));
+  row_norm2_max_kernel<<<blocks, 256, 0, s>>>(db, N, D, out);
+  T2P_LAUNCH_CHECK();
+  return T2P_OK;
+}
+
+int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                       const float* d_db_norm2_max, int force_rescan, double* d_out_scores, int64_t* d_out_idx, int32_t* d_stats,
+                       void* d_ws, size_t ws_bytes, cudaStream_t s) {
+  Arena a(d_ws, ws_bytes);
+  uint32_t* part = a.take<uint32_t>((size_t)B * p.G * p.KP);
+  float* norm_slot = a.take<float>(1);
+  T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "retrieve_topk: workspace %zu < %zu bytes", ws_bytes, a.used);
+  T2P_REQUIRE((reinterpret_cast<uintptr_t>(d_q) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_db) & 15) == 0, T2P_ERR_INVALID,
+              "retrieve_topk: q and db must be 16-byte aligned for TMA");
+  if (d_db_norm2_max == nullptr) {
+    T2P_TRY(launch_row_norm2_max(d_db, N, D, norm_slot, s));
+    d_db_norm2_max = norm_slot;
+  }
+  const int q_box = std::min(TC_QM, B), db_box = std::min(p.tile_n, N);
+  CUtensorMap tq, tdb;
+  T2P_TRY(make_tmap_rows(&tq, d_q, B, D, q_box));
+  T2P_TRY(make_tmap_rows(&tdb, d_db, N, D, db_box));
+  dim3 grid(p.G, p.qtiles);
+  if (p.KP == 16) {
+    T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
+    retrieve_scan_tc_kernel<16><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, B, N, D, p.tile_n, q_box, db_box, p.nb_bits, part);
+  } else {
+    T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
+    retrieve_scan_tc_kernel<32><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, B, N, D, p.tile_n, q_box, db_box, p.nb_bits, part);
+  }
+  T2P_LAUNCH_CHECK();
+  if (p.sel_smem > 48 * 1024)
+    T2P_CUDA(cudaFuncSetAttribute(retrieve_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sel_smem));
+  retrieve_select_kernel<<<B, SEL_THREADS, p.sel_smem, s>>>(d_q, d_db, B, N, D, p.G, p.KP, p.NC, k, p.tile_n, p.nb_bits, idx_base, part,
+                                                            d_db_norm2_max, force_rescan, d_out_scores, d_out_idx, d_stats);
+  T2P_LAUNCH_CHECK();
+  return T2P_OK;
+}
+
+}  // namespace t2p

@@ -134,8 +134,27 @@ def pack_lstm(bb: BlobBuilder, sd, prefix: str) -> _lib.LstmDesc:
     d = _lib.LstmDesc()
     d.xproj_off = bb.add(np.stack(xproj))
     d.whh_off = bb.add(np.stack(whh))
+    d.whh_reg_off = bb.add(_lstm_register_tiling(np.stack(whh))) if H in (32, 64, 128, 256) else -1
     d.vocab, d.hidden = V, H
     return d
+
+
+def _lstm_register_tiling(whh_t: np.ndarray) -> np.ndarray:
+    """whh_t [2, H, 4H] (= W_hh^T) -> [2, CS, NI, 4, 256, 4], the order in which the threads of ``lstm_reg_kernel``
+    (csrc/lstm.cu) load their register-resident slice with coalesced float4 reads: cluster rank r owns hidden units
+    [32r, 32r+32); thread w*32 + kp*4 + jj owns unit 32r + 4w + jj and the k values 4*(8i + kp) + e."""
+    H = whh_t.shape[1]
+    CS, NI = H // 32, H // 32
+    r = np.arange(CS)[:, None, None, None, None]
+    i = np.arange(NI)[None, :, None, None, None]
+    e = np.arange(4)[None, None, :, None, None]
+    t = np.arange(256)[None, None, None, :, None]
+    g = np.arange(4)[None, None, None, None, :]
+    w, kp, jj = t // 32, (t % 32) // 4, t % 4
+    k = 4 * (8 * i + kp) + e
+    col = g * H + 32 * r + 4 * w + jj
+    k, col = np.broadcast_arrays(k, col)
+    return np.stack([whh_t[d][k, col] for d in range(2)])
 
 
 def pack_superglue(bb: BlobBuilder, sd, prefix: str, layer_names, sinkhorn_iters: int, match_threshold: float) -> _lib.SuperGlueDesc:

@@ -70,6 +70,21 @@ typedef struct {
 size_t t2p_retrieve_topk_workspace(int B, int N, int D, int k);
 int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
                       double* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes, t2p_stream stream);
+/* Same, with the knobs of the tensor-core path.  When D % 32 == 0, D <= 256 and k <= 26 the scores are first
+ * computed on the tcgen05 tensor cores in TF32 (TMA-fed scan with an in-kernel top-k); the candidates are then
+ * re-scored in float64 and the result is CERTIFIED against the TF32 error bound eps*|q|*max|d|, with an exact
+ * float64 rescan of the DB for any query that cannot be certified -- the output is always the float64 ranking.
+ * Other shapes take the exact-fp32 CUDA-core scan.
+ *   d_db_norm2_max: device scalar = max squared row norm of the DB (t2p_db_row_norm2_max, computed once per DB);
+ *                   NULL = compute it inside the call (one extra pass over the DB);
+ *   flags:          T2P_RETRIEVE_*;
+ *   d_stats:        optional device int32[2]: [0] += queries certified on the tensor path, [1] += queries rescanned. */
+#define T2P_RETRIEVE_FORCE_GENERIC 1 /* always use the CUDA-core scan */
+#define T2P_RETRIEVE_FORCE_RESCAN 2  /* tensor path, but treat every query as uncertified (tests the rescan) */
+int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                         const float* d_db_norm2_max, int flags, double* d_out_scores, int64_t* d_out_idx,
+                         int32_t* d_stats, void* d_ws, size_t ws_bytes, t2p_stream stream);
+int t2p_db_row_norm2_max(const float* d_db, int N, int D, float* d_out, t2p_stream stream);
 /* merge R per-shard lists [R,B,k_in] (e.g. after an all-gather) into [B,k_out], same ordering rule */
 int t2p_topk_merge(const double* d_scores, const int64_t* d_idx, int R, int B, int k_in, int k_out,
                    double* d_out_scores, int64_t* d_out_idx, t2p_stream stream);

@@ -75,3 +75,69 @@ def test_full_size_properties():
     assert torch.equal(idx, idx2) and torch.equal(sc, sc2)
     ids = cdb.topk_ids(q[:2], 3)
     assert ids.shape == (2, 3) and ids[0, 0] == "0010_00000"
+
+
+# ---- tensor-core (tcgen05 + TMA) scan: certified TF32 candidates, float64 re-rank, exact rescan ---------------------
+from text2pos_cvpr2022_b200 import _lib  # noqa: E402
+from text2pos_cvpr2022_b200.retrieval import db_row_norm2_max  # noqa: E402
+
+
+def _check_flags(db, q, k, flags, expect_rescans=None, idx_base=0):
+    stats = torch.zeros(2, dtype=torch.int32, device="cuda")
+    idx, sc = retrieve_topk(q.cuda(), db.cuda(), k, idx_base, flags=flags, stats=stats)
+    ref_i, ref_s = oracle.retrieval.topk(db.numpy(), q.numpy(), min(k, db.shape[0]))
+    kk = ref_i.shape[1]
+    np.testing.assert_array_equal(idx.cpu().numpy()[:, :kk], ref_i + idx_base)
+    np.testing.assert_allclose(sc.cpu().numpy()[:, :kk], ref_s, rtol=1e-12, atol=1e-15)
+    st = stats.cpu().tolist()
+    if flags & _lib.RETRIEVE_FORCE_GENERIC:
+        assert st == [0, 0]
+    else:
+        assert st[0] + st[1] == q.shape[0]  # every query either certified on the tensor path or rescanned exactly
+        if expect_rescans is not None:
+            assert st[1] == expect_rescans, st
+    return st
+
+
+@pytest.mark.parametrize("B,N,D,k", [(64, 10000, 256, 10), (64, 12500, 256, 10), (1, 128, 256, 10), (130, 3000, 128, 5),
+                                      (7, 50, 32, 10), (3, 5, 64, 10), (64, 100000, 256, 10), (20, 2500, 96, 26), (64, 20000, 256, 1)])
+def test_tensor_core_path_equals_float64_oracle(B, N, D, k):
+    db = syn.synth_db_embeddings(N + D + 1, N, D)
+    q = syn.synth_query_embeddings(B + 2, B, D)
+    st = _check_flags(db, q, k, 0)
+    if N >= 1000:  # well separated synthetic scores: the TF32 candidates certify, no rescan needed
+        assert st[1] == 0, st
+    _check_flags(db, q, k, _lib.RETRIEVE_FORCE_GENERIC)
+
+
+def test_tensor_core_forced_rescan_is_exact():
+    db = syn.synth_db_embeddings(3, 4000, 256)
+    q = syn.synth_query_embeddings(4, 9, 256)
+    _check_flags(db, q, 10, _lib.RETRIEVE_FORCE_RESCAN, expect_rescans=9, idx_base=777)
+
+
+def test_tensor_core_dense_scores_fall_back_to_the_exact_rescan():
+    """Rows that differ from the query direction by tiny perturbations: the scores near the top are closer together than
+    the TF32 error bound, so TF32 cannot rank them; the certification must notice and the result must still be exact."""
+    g = torch.Generator().manual_seed(11)
+    q = torch.nn.functional.normalize(torch.randn(4, 256, generator=g))
+    db = torch.nn.functional.normalize(q[0:1] + 0.02 * torch.randn(6000, 256, generator=g))
+    db[17] = db[4000]  # exact duplicates on top of it
+    st = _check_flags(db, q, 10, 0)
+    assert st[1] >= 1, st  # at least the query aligned with the cluster needs the rescan
+
+
+def test_tensor_core_unnormalised_rows_and_negative_scores():
+    g = torch.Generator().manual_seed(12)
+    db = torch.randn(5000, 64, generator=g) * torch.rand(5000, 1, generator=g) * 3.0  # norms vary, scores of both signs
+    q = torch.randn(33, 64, generator=g)
+    _check_flags(db, q, 10, 0)
+    db_neg = -torch.abs(db)  # every score against a positive query is negative
+    _check_flags(db_neg, torch.abs(q), 7, 0)
+
+
+def test_db_row_norm2_max_kernel():
+    db = syn.synth_db_embeddings(5, 3000, 256) * 1.7
+    got = float(db_row_norm2_max(db.cuda()).cpu())
+    want = float((db.double() ** 2).sum(1).max())
+    assert abs(got - want) <= 1e-5 * want

@@ -18,6 +18,8 @@ KNN_K = 8
 MAX_GNN_LAYERS = 32
 
 T2P_OK = 0
+RETRIEVE_FORCE_GENERIC = 1
+RETRIEVE_FORCE_RESCAN = 2
 
 
 class LinearDesc(C.Structure):
@@ -96,6 +98,8 @@ PROTOTYPES = {
     "t2p_weights_device_ptr": (_P, [_P]),
     "t2p_retrieve_topk_workspace": (_SZ, [_I, _I, _I, _I]),
     "t2p_retrieve_topk": (_I, [_P, _P, _I, _I, _I, _I, C.c_int64, _P, _P, _P, _SZ, _P]),
+    "t2p_retrieve_topk_ex": (_I, [_P, _P, _I, _I, _I, _I, C.c_int64, _P, _I, _P, _P, _P, _P, _SZ, _P]),
+    "t2p_db_row_norm2_max": (_I, [_P, _I, _I, _P, _P]),
     "t2p_topk_merge": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "t2p_fps": (_I, [_P, _I, _I, _I, _P, _P]),
     "t2p_ball_query": (_I, [_P, _P, _I, _I, _I, C.c_float, _I, _P, _P, _P]),

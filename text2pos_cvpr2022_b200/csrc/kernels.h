@@ -35,4 +35,18 @@ int launch_fps_ball_mode(const float* pos, int n_obj, int P, int m, float r2, in
 int launch_knn_cells(const float* e, const int32_t* cell_offsets, int n_cells, int max_cell_objects, int D,
                      int32_t* knn, int32_t* obj_cell, cudaStream_t s);
 
+
+// tensor-core (tcgen05 + TMA) retrieval path, csrc/retrieval_tc.cu
+struct TcPlan {
+  bool ok;
+  int KP, NC, tile_n, tiles, G, tiles_per_cta, nb_bits, qtiles;
+  size_t scan_smem, sel_smem;
+};
+TcPlan tc_plan(int B, int N, int D, int k, int sms);
+size_t tc_workspace_bytes(const TcPlan& p, int B);
+int launch_row_norm2_max(const float* db, int N, int D, float* out, cudaStream_t s);
+int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                       const float* d_db_norm2_max, int force_rescan, double* d_out_scores, int64_t* d_out_idx, int32_t* d_stats,
+                       void* d_ws, size_t ws_bytes, cudaStream_t s);
+
 }  // namespace t2p

@@ -284,16 +284,20 @@ extern "C" {
 
 size_t t2p_retrieve_topk_workspace(int B, int N, int D, int k) {
   if (B <= 0 || N <= 0 || D <= 0 || k <= 0) return 0;
-  // G never exceeds the SM count of any sm_100 part we target (<= 160)
+  // generic path: G never exceeds the SM count of any sm_100 part we target (<= 160)
   const size_t G = 160;
   const size_t kp = std::min(RT_MAX_KP, k + 6);
-  return align_up(G * B * kp * sizeof(float), 256) + align_up(G * B * kp * sizeof(int32_t), 256);
+  size_t generic = align_up(G * B * kp * sizeof(float), 256) + align_up(G * B * kp * sizeof(int32_t), 256);
+  size_t tc = 0;
+  for (int sms = 64; sms <= 160; sms += 4) {  // the plan depends on the SM count; size for the worst case
+    const TcPlan p = tc_plan(B, N, D, k, sms);
+    if (p.ok) tc = std::max(tc, tc_workspace_bytes(p, B));
+  }
+  return std::max(generic, tc);
 }
 
-int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
-                      double* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes, t2p_stream stream) {
-  T2P_REQUIRE(d_q && d_db && d_out_scores && d_out_idx, T2P_ERR_INVALID, "retrieve_topk: null argument");
-  T2P_REQUIRE(B > 0 && N > 0 && D > 0, T2P_ERR_INVALID, "retrieve_topk: B=%d N=%d D=%d must be positive", B, N, D);
+static int retrieve_generic(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                            double* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes, cudaStream_t s) {
   T2P_REQUIRE(k >= 1 && k + 6 <= RT_MAX_KP, T2P_ERR_UNSUPPORTED, "retrieve_topk: k=%d outside [1,%d]", k, RT_MAX_KP - 6);
   const int sms = std::min(160, cached_sm_count());
   const RetrievePlan p = make_plan(B, N, D, k, sms);
@@ -301,7 +305,6 @@ int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, 
   float* part_s = a.take<float>((size_t)p.G * B * p.kp);
   int32_t* part_i = a.take<int32_t>((size_t)p.G * B * p.kp);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "retrieve_topk: workspace %zu < %zu bytes", ws_bytes, a.used);
-  cudaStream_t s = as_stream(stream);
   T2P_CUDA(cudaFuncSetAttribute(retrieve_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid(p.G, p.qtiles);
   retrieve_partial_kernel<<<grid, 16 * p.RG, p.smem, s>>>(d_q, d_db, B, N, D, p.rows_per_cta, p.RG, p.kp, part_s, part_i);
@@ -309,6 +312,31 @@ int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, 
   retrieve_merge_kernel<<<B, 128, 0, s>>>(d_q, d_db, B, N, D, p.G, p.kp, k, idx_base, part_s, part_i, d_out_scores, d_out_idx);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
+}
+
+int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                         const float* d_db_norm2_max, int flags, double* d_out_scores, int64_t* d_out_idx, int32_t* d_stats,
+                         void* d_ws, size_t ws_bytes, t2p_stream stream) {
+  T2P_REQUIRE(d_q && d_db && d_out_scores && d_out_idx, T2P_ERR_INVALID, "retrieve_topk: null argument");
+  T2P_REQUIRE(B > 0 && N > 0 && D > 0, T2P_ERR_INVALID, "retrieve_topk: B=%d N=%d D=%d must be positive", B, N, D);
+  cudaStream_t s = as_stream(stream);
+  if (!(flags & T2P_RETRIEVE_FORCE_GENERIC)) {
+    const TcPlan p = tc_plan(B, N, D, k, std::min(160, cached_sm_count()));
+    if (p.ok)
+      return launch_retrieve_tc(p, d_q, d_db, B, N, D, k, idx_base, d_db_norm2_max, (flags & T2P_RETRIEVE_FORCE_RESCAN) ? 1 : 0,
+                                d_out_scores, d_out_idx, d_stats, d_ws, ws_bytes, s);
+  }
+  return retrieve_generic(d_q, d_db, B, N, D, k, idx_base, d_out_scores, d_out_idx, d_ws, ws_bytes, s);
+}
+
+int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
+                      double* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes, t2p_stream stream) {
+  return t2p_retrieve_topk_ex(d_q, d_db, B, N, D, k, idx_base, nullptr, 0, d_out_scores, d_out_idx, nullptr, d_ws, ws_bytes, stream);
+}
+
+int t2p_db_row_norm2_max(const float* d_db, int N, int D, float* d_out, t2p_stream stream) {
+  T2P_REQUIRE(d_db && d_out && N > 0 && D > 0, T2P_ERR_INVALID, "db_row_norm2_max: bad argument");
+  return launch_row_norm2_max(d_db, N, D, d_out, as_stream(stream));
 }
 
 int t2p_topk_merge(const double* d_scores, const int64_t* d_idx, int R, int B, int k_in, int k_out, double* d_out_scores,

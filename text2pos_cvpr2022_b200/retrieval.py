@@ -14,8 +14,25 @@ import torch
 from . import _lib
 
 
-def retrieve_topk(q: torch.Tensor, db: torch.Tensor, k: int, idx_base: int = 0, workspace: Optional[_lib.Workspace] = None):
-    """q [B,D], db [N,D] float32 CUDA -> (idx [B,k] int64, scores [B,k] float64)."""
+def db_row_norm2_max(db: torch.Tensor) -> torch.Tensor:
+    """Device scalar (float32 [1]) = max squared row norm of ``db``: the certification bound of the tensor-core scan.
+    Computed once per database (``t2p_db_row_norm2_max``)."""
+    lib = _lib.load()
+    _lib.require_cuda(db, "cell database")
+    db = db.float().contiguous()
+    out = torch.zeros(1, dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(lib.t2p_db_row_norm2_max(_lib.ptr(db), db.shape[0], db.shape[1], _lib.ptr(out), _lib.stream_ptr(db.device)),
+                   "db_row_norm2_max")
+    return out
+
+
+def retrieve_topk(q: torch.Tensor, db: torch.Tensor, k: int, idx_base: int = 0, workspace: Optional[_lib.Workspace] = None,
+                  norm2_max: Optional[torch.Tensor] = None, flags: int = 0, stats: Optional[torch.Tensor] = None):
+    """q [B,D], db [N,D] float32 CUDA -> (idx [B,k] int64, scores [B,k] float64).
+
+    ``norm2_max``: optional result of :func:`db_row_norm2_max` (saves one pass over the DB per call on the tensor-core
+    path); ``flags``: ``_lib.RETRIEVE_FORCE_*``; ``stats``: optional int32 [2] device counters (certified, rescanned)."""
     lib = _lib.load()
     _lib.require_cuda(q, "queries")
     _lib.require_cuda(db, "cell database")
@@ -28,12 +45,15 @@ def retrieve_topk(q: torch.Tensor, db: torch.Tensor, k: int, idx_base: int = 0, 
     dev = q.device
     out_s = torch.empty(B, k, dtype=torch.float64, device=dev)
     out_i = torch.empty(B, k, dtype=torch.int64, device=dev)
+    if B == 0:
+        return out_i, out_s
     ws_owner = workspace if workspace is not None else _lib.Workspace()
     with torch.cuda.device(dev):
         ws = ws_owner.get(lib.t2p_retrieve_topk_workspace(B, N, D, k), dev)
         _lib.check(
-            lib.t2p_retrieve_topk(_lib.ptr(q), _lib.ptr(db), B, N, D, k, int(idx_base), _lib.ptr(out_s), _lib.ptr(out_i),
-                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+            lib.t2p_retrieve_topk_ex(_lib.ptr(q), _lib.ptr(db), B, N, D, k, int(idx_base), _lib.ptr(norm2_max), int(flags),
+                                     _lib.ptr(out_s), _lib.ptr(out_i), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr(dev)),
             "retrieve_topk",
         )
     return out_i, out_s
@@ -66,12 +86,13 @@ class CellDatabase:
         self.cell_ids = None if cell_ids is None else np.asarray(cell_ids)
         self.idx_base = int(idx_base)
         self._ws = _lib.Workspace()
+        self.norm2_max = db_row_norm2_max(self.embeddings) if len(self) else None
 
     def __len__(self):
         return self.embeddings.shape[0]
 
     def topk(self, queries: torch.Tensor, k: int):
-        return retrieve_topk(queries, self.embeddings, k, self.idx_base, self._ws)
+        return retrieve_topk(queries, self.embeddings, k, self.idx_base, self._ws, self.norm2_max)
 
     def topk_ids(self, queries: torch.Tensor, k: int) -> np.ndarray:
         """-> [B,k] array of cell-id strings, what ``eval_epoch`` stores in ``top_retrievals``."""
@@ -109,6 +130,7 @@ class ShardedCellDatabase:
         self._local_topk = local_topk
         self._merge = merge
         self._ws = None if local_topk is not None else _lib.Workspace()
+        self._norm2_max = db_row_norm2_max(local_embeddings) if (local_topk is None and self.hi > self.lo) else None
 
     def topk(self, queries: torch.Tensor, k: int):
         """queries [B,D] replicated on every rank -> (idx [B,k] global int64, scores [B,k] float64) on every rank."""
@@ -118,7 +140,7 @@ class ShardedCellDatabase:
             if self._local_topk is not None:
                 li, ls = self._local_topk(queries, self.local, k, self.lo)
             else:
-                li, ls = retrieve_topk(queries, self.local, k, self.lo, self._ws)
+                li, ls = retrieve_topk(queries, self.local, k, self.lo, self._ws, self._norm2_max)
         else:  # empty shard
             li = torch.full((B, k), -1, dtype=torch.int64, device=dev)
             ls = torch.full((B, k), float("-inf"), dtype=torch.float64, device=dev)

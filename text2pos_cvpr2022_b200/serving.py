@@ -46,6 +46,10 @@ class OnlineRetrievalEngine:
     def set_db(self, db: torch.Tensor):
         _lib.require_cuda(db, "cell database")
         self.db = db.float().contiguous()
+        from .retrieval import db_row_norm2_max
+
+        self.db_norm2_max = db_row_norm2_max(self.db)  # once per DB: certification bound of the tensor-core scan
+        self.stats = torch.zeros(2, dtype=torch.int32, device=self.device)  # [certified, rescanned] query counters
         with torch.cuda.device(self.device):
             n = self.lib.t2p_retrieve_topk_workspace(self.B, self.db.shape[0], self.db.shape[1], self.k)
             self.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=self.device)
@@ -60,11 +64,13 @@ class OnlineRetrievalEngine:
         )
 
     def enqueue_topk(self, db: Optional[torch.Tensor] = None):
+        """``db``: an alternative resident copy with the SAME rows (hence the same norm bound) as ``self.db``."""
         db = self.db if db is None else db
         _lib.check(
-            self.lib.t2p_retrieve_topk(self.q.data_ptr(), db.data_ptr(), self.B, db.shape[0], db.shape[1], self.k,
-                                       self.idx_base, self.out_scores.data_ptr(), self.out_idx.data_ptr(),
-                                       self.ws_topk.data_ptr(), self.ws_topk.numel(), _lib.stream_ptr(self.device)),
+            self.lib.t2p_retrieve_topk_ex(self.q.data_ptr(), db.data_ptr(), self.B, db.shape[0], db.shape[1], self.k,
+                                          self.idx_base, self.db_norm2_max.data_ptr(), 0, self.out_scores.data_ptr(),
+                                          self.out_idx.data_ptr(), self.stats.data_ptr(), self.ws_topk.data_ptr(),
+                                          self.ws_topk.numel(), _lib.stream_ptr(self.device)),
             "retrieve_topk",
         )
 

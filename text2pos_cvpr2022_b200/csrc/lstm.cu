@@ -178,23 +178,63 @@ lstm_finalize_kernel(const float* __restrict__ hfinal, int B, int H, int normali
 // ---------------------------------------------------------------------------------------------------
 // Register-resident variant (H in {32,64,128,256}): the recurrent matrix never leaves the register file.
 //
-// Cluster of CS = H/32 CTAs per (direction, group of 8 sequences); CTA rank r owns hidden units
+// Cluster of CS = H/32 CTAs per (direction, group of NB sequences); CTA rank r owns hidden units
 // [32r, 32r+32) = 128 gate columns.  256 threads; thread (warp w, lane = kp*4 + jj) owns the 4 gates of unit
 // j = 4w + jj for the k values {4*(8i + kp) + e : i < H/32, e < 4} (H/8 of the H inputs), i.e. H/2 <= 128
-// weights in registers.  One step = H/8 broadcast float4 reads of h per sequence, 4*H FMAs per thread,
-// a 3-stage recursive-halving reduce-scatter over the 8 kp lanes (28 shuffles) that leaves lane kp with
-// the four complete gate pre-activations of sequence b = kp, the cell update in registers, a float4
-// gather over the 4 jj lanes and one 16-byte DSMEM store per peer CTA, then one cluster barrier.
+// weights in registers.  One step = H/8 broadcast float4 reads of h per sequence, 4*H*NB/8 FMAs per thread,
+// a 3-stage recursive-halving reduce-scatter over the 8 kp lanes (28 shuffles) that leaves lane kp with the
+// four complete gate pre-activations of sequence b = kp (sequences 8..NB-1: an xor butterfly, lane kp < NB-8
+// takes sequence 8+kp), the cell update in registers, a float4 gather over the 4 jj lanes and one 16-byte
+// st.async per peer CTA.  The step hand-off is an mbarrier per h buffer in every CTA: the st.async stores of all
+// CS CTAs complete NB*H*4 transaction bytes on it, so no cluster-wide barrier / memory fence sits on the
+// critical path.  B200 co-schedules at most 15 clusters of 8 CTAs (ncu launch__cluster_max_active), so NB is
+// chosen by the host such that 2*ceil(B/NB) <= 14 whenever possible (NB = 10 for B = 64).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lstm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void lstm_bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lstm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lstm_bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lstm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lstm_bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = lstm_smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();  // a protocol bug must not hang the GPU
+  }
+}
 
-template <int H>
+template <int H, int NB>
 __global__ void __launch_bounds__(256, 1)
 lstm_reg_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_reg, const int32_t* __restrict__ tokens,
                 const int32_t* __restrict__ lengths, int B, int T, int V, float* __restrict__ hfinal) {
   constexpr int CS = H / 32;  // CTAs per cluster
   constexpr int NI = H / 32;  // float4 chunks of h per thread and sequence
+  constexpr int NX = NB - 8;  // sequences beyond the 8 handled by the reduce-scatter
+  static_assert(NX >= 0 && NX <= 4, "NB in [8,12]");
   extern __shared__ __align__(16) float lstm_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -203,11 +243,13 @@ lstm_reg_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_r
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int kp = lane >> 2, jj = lane & 3;
   const int u0 = rank * 32, j = 4 * w + jj;
-  const int b0 = group * LSTM_NB;
+  const int b0 = group * NB;
 
-  float* hbuf = lstm_smem;                                    // [2][NB][H]
-  int* tok = reinterpret_cast<int*>(hbuf + 2 * LSTM_NB * H);  // [NB][T]
-  int* len = tok + LSTM_NB * T;                               // [NB]
+  float* hbuf = lstm_smem;                                          // [2][NB][H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + 2 * NB * H);  // [2]
+  int* tok = reinterpret_cast<int*>(bars + 2);                      // [NB][T]
+  int* len = tok + NB * T;                                          // [NB]
+  constexpr uint32_t STEP_BYTES = (uint32_t)NB * H * sizeof(float);
 
   // register-resident weights: Wr[i][e] = the 4 gates (i,f,g,o) of unit j for k = 4*(8i + kp) + e
   float4 Wr[NI][4];
@@ -218,52 +260,78 @@ lstm_reg_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_r
 #pragma unroll
       for (int e = 0; e < 4; ++e) Wr[i][e] = __ldg(src + (size_t)(i * 4 + e) * 256);
   }
-  for (int t = tid; t < 2 * LSTM_NB * H; t += 256) hbuf[t] = 0.f;
-  for (int t = tid; t < LSTM_NB * T; t += 256) {
+  for (int t = tid; t < 2 * NB * H; t += 256) hbuf[t] = 0.f;
+  for (int t = tid; t < NB * T; t += 256) {
     const int b = t / T, tt = t - b * T;
     const int v = (b0 + b < B) ? tokens[(size_t)(b0 + b) * T + tt] : 0;
     tok[t] = (v < 0 || v >= V) ? 0 : v;
   }
-  if (tid < LSTM_NB) len[tid] = (b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
+  if (tid < NB) len[tid] = (b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
+  if (tid == 0) {
+    lstm_bar_init(&bars[0], 1);
+    lstm_bar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    lstm_bar_expect(&bars[0], STEP_BYTES);  // armed for their first use (steps 2 and 1)
+    lstm_bar_expect(&bars[1], STEP_BYTES);
+  }
   __syncthreads();
   int max_len = 0;
 #pragma unroll
-  for (int b = 0; b < LSTM_NB; ++b) max_len = max(max_len, len[b]);
-  const int my_len = len[kp];  // this lane finalises sequence b = kp
-  cluster_arrive_release();    // every CTA of the cluster is initialised before remote h writes start
+  for (int b = 0; b < NB; ++b) max_len = max(max_len, len[b]);
+  const int len1 = len[kp];                         // this lane finalises sequence kp ...
+  const int len2 = (kp < NX) ? len[8 + kp] : 0;     // ... and sequence 8 + kp when it exists
+  cluster_arrive_release();  // barriers initialised and h buffers zeroed in every CTA before remote stores start
   cluster_wait_acquire();
 
   const float* xp_base = xproj + (size_t)dir * V * 4 * H + u0 + j;
-  auto token_at = [&](int step) -> int {
-    if (step >= my_len) return 0;
-    return tok[kp * T + (dir ? (my_len - 1 - step) : step)];
+  auto token_at = [&](int b, int L, int step) -> int {
+    if (step >= L) return 0;
+    return tok[b * T + (dir ? (L - 1 - step) : step)];
   };
-  float xn[4];
+  float xn1[4], xn2[4];
   {
-    const float* xp = xp_base + (size_t)token_at(0) * 4 * H;
+    const float* xp = xp_base + (size_t)token_at(kp, len1, 0) * 4 * H;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) xn[g] = __ldg(xp + g * H);
+    for (int g = 0; g < 4; ++g) xn1[g] = __ldg(xp + g * H);
+    if (NX > 0) {
+      const float* xq = xp_base + (size_t)token_at(kp < NX ? 8 + kp : 0, len2, 0) * 4 * H;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) xn2[g] = __ldg(xq + g * H);
+    }
   }
-  float c_state = 0.f, h_state = 0.f;
+  float c1 = 0.f, h1 = 0.f, c2 = 0.f, h2 = 0.f;
+  const uint32_t hbuf_addr = lstm_smem_u32(hbuf), bars_addr = lstm_smem_u32(bars);
 
   for (int step = 0; step < max_len; ++step) {
-    const float* hcur = hbuf + (size_t)(step & 1) * LSTM_NB * H + 4 * kp;
-    float* hnext = hbuf + (size_t)((step + 1) & 1) * LSTM_NB * H;
-    float xg[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) xg[g] = xn[g];
-    if (step + 1 < max_len) {  // next step's input projection: L2 latency hidden behind the FMAs below
-      const float* xp = xp_base + (size_t)token_at(step + 1) * 4 * H;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) xn[g] = __ldg(xp + g * H);
+    const int cur = step & 1, nxt = cur ^ 1;
+    if (step > 0) {  // h_{step-1} from every CTA of the cluster has landed in hbuf[cur]
+      lstm_bar_wait(&bars[cur], (uint32_t)(((step - 1) >> 1) & 1));
+      if (tid == 0) lstm_bar_expect(&bars[cur], STEP_BYTES);  // re-arm for step + 2
     }
-    float acc[LSTM_NB][4];
+    const float* hcur = hbuf + (size_t)cur * NB * H + 4 * kp;
+    float xg1[4], xg2[4];
 #pragma unroll
-    for (int b = 0; b < LSTM_NB; ++b)
+    for (int g = 0; g < 4; ++g) {
+      xg1[g] = xn1[g];
+      xg2[g] = xn2[g];
+    }
+    if (step + 1 < max_len) {  // next step's input projection: L2 latency hidden behind the FMAs below
+      const float* xp = xp_base + (size_t)token_at(kp, len1, step + 1) * 4 * H;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) xn1[g] = __ldg(xp + g * H);
+      if (NX > 0) {
+        const float* xq = xp_base + (size_t)token_at(kp < NX ? 8 + kp : 0, len2, step + 1) * 4 * H;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xn2[g] = __ldg(xq + g * H);
+      }
+    }
+    float acc[NB][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int g = 0; g < 4; ++g) acc[b][g] = 0.f;
 #pragma unroll
-    for (int b = 0; b < LSTM_NB; ++b) {
+    for (int b = 0; b < NB; ++b) {
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 32 * i);
@@ -277,8 +345,8 @@ lstm_reg_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_r
         }
       }
     }
-    // reduce-scatter over the 8 kp lanes: lane kp ends with the gates of sequence b = kp
-    float r1[4][4], r2[2][4], gate[4];
+    // sequences 0..7: reduce-scatter over the 8 kp lanes, lane kp ends with the gates of sequence kp
+    float r1[4][4], r2[2][4], gate1[4], gate2[4];
     {
       const bool up = (kp & 4) != 0;
 #pragma unroll
@@ -307,43 +375,79 @@ lstm_reg_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_r
       for (int g = 0; g < 4; ++g) {
         const float send = up ? r2[0][g] : r2[1][g];
         const float keep = up ? r2[1][g] : r2[0][g];
-        gate[g] = keep + __shfl_xor_sync(0xffffffffu, send, 4) + xg[g];
+        gate1[g] = keep + __shfl_xor_sync(0xffffffffu, send, 4) + xg1[g];
       }
     }
-    if (step < my_len) {
-      const float ig = sigmoidf_(gate[0]);
-      const float fg = sigmoidf_(gate[1]);
-      const float gg = tanhf(gate[2]);
-      const float og = sigmoidf_(gate[3]);
-      c_state = fmaf(fg, c_state, ig * gg);
-      h_state = og * tanhf(c_state);
-    }
-    // h_t[b = kp][u0 + 4w .. +3] gathered over the 4 jj lanes, then one float4 per peer CTA
-    float4 hv4;
-    hv4.x = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 0);
-    hv4.y = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 1);
-    hv4.z = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 2);
-    hv4.w = __shfl_sync(0xffffffffu, h_state, (lane & ~3) | 3);
-    float* dst_local = hnext + kp * H + u0 + 4 * w;
+    // sequences 8..NB-1: xor butterfly (every lane gets every sum), lane kp < NX takes sequence 8 + kp
+    if (NX > 0) {
 #pragma unroll
-    for (int r = jj; r < CS; r += 4) {
-      float* remote = cluster.map_shared_rank(dst_local, r);
-      *reinterpret_cast<float4*>(remote) = hv4;
+      for (int g = 0; g < 4; ++g) gate2[g] = 0.f;
+#pragma unroll
+      for (int x = 0; x < NX; ++x)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v = acc[8 + x][g];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          if (kp == x) gate2[g] = v + xg2[g];
+        }
     }
-    cluster_arrive_release();  // h_t complete in every CTA; also orders this step's reads before the next overwrite
-    cluster_wait_acquire();
+    if (step < len1) {
+      const float ig = sigmoidf_(gate1[0]);
+      const float fg = sigmoidf_(gate1[1]);
+      const float gg = tanhf(gate1[2]);
+      const float og = sigmoidf_(gate1[3]);
+      c1 = fmaf(fg, c1, ig * gg);
+      h1 = og * tanhf(c1);
+    }
+    if (NX > 0 && step < len2) {
+      const float ig = sigmoidf_(gate2[0]);
+      const float fg = sigmoidf_(gate2[1]);
+      const float gg = tanhf(gate2[2]);
+      const float og = sigmoidf_(gate2[3]);
+      c2 = fmaf(fg, c2, ig * gg);
+      h2 = og * tanhf(c2);
+    }
+    if (step + 1 < max_len) {
+      // h_t[b][u0 + 4w .. +3] gathered over the 4 jj lanes, then one 16-byte st.async per peer CTA
+      const uint32_t dst_bar = bars_addr + (uint32_t)nxt * 8u;
+      float4 hv4;
+      hv4.x = __shfl_sync(0xffffffffu, h1, (lane & ~3) | 0);
+      hv4.y = __shfl_sync(0xffffffffu, h1, (lane & ~3) | 1);
+      hv4.z = __shfl_sync(0xffffffffu, h1, (lane & ~3) | 2);
+      hv4.w = __shfl_sync(0xffffffffu, h1, (lane & ~3) | 3);
+      const uint32_t dst1 = hbuf_addr + (uint32_t)(((nxt * NB + kp) * H + u0 + 4 * w) * sizeof(float));
+#pragma unroll
+      for (int r = jj; r < CS; r += 4) st_async_v4(map_to_rank(dst1, r), hv4, map_to_rank(dst_bar, r));
+      if (NX > 0) {
+        float4 hx4;
+        hx4.x = __shfl_sync(0xffffffffu, h2, (lane & ~3) | 0);
+        hx4.y = __shfl_sync(0xffffffffu, h2, (lane & ~3) | 1);
+        hx4.z = __shfl_sync(0xffffffffu, h2, (lane & ~3) | 2);
+        hx4.w = __shfl_sync(0xffffffffu, h2, (lane & ~3) | 3);
+        if (kp < NX) {
+          const uint32_t dst2 = hbuf_addr + (uint32_t)(((nxt * NB + 8 + kp) * H + u0 + 4 * w) * sizeof(float));
+#pragma unroll
+          for (int r = jj; r < CS; r += 4) st_async_v4(map_to_rank(dst2, r), hx4, map_to_rank(dst_bar, r));
+        }
+      }
+    }
   }
-  if (b0 + kp < B) hfinal[((size_t)dir * B + b0 + kp) * H + u0 + j] = h_state;
+  if (b0 + kp < B) hfinal[((size_t)dir * B + b0 + kp) * H + u0 + j] = h1;
+  if (NX > 0 && kp < NX && b0 + 8 + kp < B) hfinal[((size_t)dir * B + b0 + 8 + kp) * H + u0 + j] = h2;
+  cluster_arrive_release();  // no CTA exits while a peer may still store into its shared memory
+  cluster_wait_acquire();
 }
 
-template <int H>
+template <int H, int NB>
 static int lstm_reg_launch(const float* xproj, const float* whh_reg, const int32_t* tokens, const int32_t* lengths, int B,
                            int T, int V, float* hfinal, cudaStream_t s) {
-  auto kern = lstm_reg_kernel<H>;
-  const size_t smem = (size_t)2 * LSTM_NB * H * sizeof(float) + ((size_t)LSTM_NB * T + LSTM_NB) * sizeof(int);
+  auto kern = lstm_reg_kernel<H, NB>;
+  const size_t smem = (size_t)2 * NB * H * sizeof(float) + 2 * sizeof(uint64_t) + ((size_t)NB * T + NB) * sizeof(int);
   T2P_REQUIRE(smem <= 200 * 1024, T2P_ERR_UNSUPPORTED, "lstm_encode: T=%d needs %zu bytes of shared memory", T, smem);
   if (smem > 48 * 1024) T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int groups = (B + LSTM_NB - 1) / LSTM_NB;
+  const int groups = (B + NB - 1) / NB;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * 2 * (H / 32));
   cfg.blockDim = dim3(256);
@@ -358,6 +462,17 @@ static int lstm_reg_launch(const float* xproj, const float* whh_reg, const int32
   cfg.numAttrs = 1;
   T2P_CUDA(cudaLaunchKernelEx(&cfg, kern, xproj, whh_reg, tokens, lengths, B, T, V, hfinal));
   return T2P_OK;
+}
+
+// sequences per cluster: the smallest NB in {8,10,12} that needs at most 14 clusters of H/32 CTAs (B200 co-schedules 15
+// clusters of 8); 12 beyond that (several waves)
+template <int H>
+static int lstm_reg_dispatch(const float* xproj, const float* whh_reg, const int32_t* tokens, const int32_t* lengths, int B,
+                             int T, int V, float* hfinal, cudaStream_t s) {
+  const int max_clusters = (H == 256) ? 14 : 28;
+  if (2 * ((B + 7) / 8) <= max_clusters) return lstm_reg_launch<H, 8>(xproj, whh_reg, tokens, lengths, B, T, V, hfinal, s);
+  if (2 * ((B + 9) / 10) <= max_clusters) return lstm_reg_launch<H, 10>(xproj, whh_reg, tokens, lengths, B, T, V, hfinal, s);
+  return lstm_reg_launch<H, 12>(xproj, whh_reg, tokens, lengths, B, T, V, hfinal, s);
 }
 
 struct LstmPlan {
@@ -438,10 +553,10 @@ int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32
     float* hfinal = a.take<float>((size_t)2 * B * H);
     T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "lstm_encode: workspace %zu < %zu bytes", ws_bytes, a.used);
     const float* wr = wptr(w, desc->whh_reg_off);
-    if (H == 256) T2P_TRY(lstm_reg_launch<256>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
-    else if (H == 128) T2P_TRY(lstm_reg_launch<128>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
-    else if (H == 64) T2P_TRY(lstm_reg_launch<64>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
-    else T2P_TRY(lstm_reg_launch<32>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    if (H == 256) T2P_TRY(lstm_reg_dispatch<256>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else if (H == 128) T2P_TRY(lstm_reg_dispatch<128>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else if (H == 64) T2P_TRY(lstm_reg_dispatch<64>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else T2P_TRY(lstm_reg_dispatch<32>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
     lstm_finalize_kernel<<<(B + 7) / 8, 256, 0, s>>>(hfinal, B, H, normalize, d_out);
     T2P_LAUNCH_CHECK();
     return T2P_OK;

@@ -227,8 +227,8 @@ __device__ __forceinline__ double warp_dot_f64(const float* __restrict__ q_smem,
 }
 
 struct SelSmem {
-  unsigned hist[256];
-  unsigned sel_prefix, sel_remaining, n_cand, below_max, m_last, fallback;
+  unsigned wsum[2][SEL_THREADS / 32];
+  unsigned n_cand, below_max, m_last, fallback;
   double tk, qq;
   uint32_t cand_key[SEL_CAND_MAX];
   int32_t cand_row[SEL_CAND_MAX];
@@ -257,8 +257,6 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
     for (int t = tid; t < total; t += SEL_THREADS) keys[t] = src[t];
   }
   if (tid == 0) {
-    sm->sel_prefix = 0;
-    sm->sel_remaining = (unsigned)NC;
     sm->n_cand = 0;
     sm->below_max = 0;
     sm->m_last = 0;
@@ -268,81 +266,81 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
   }
   __syncthreads();
 
-  // radix select (4 x 8 bits, most significant first): tau = NC-th largest key
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    sm->hist[tid] = 0;
+  // tau = NC-th largest key, by bisection on the key bits (32 rounds of "how many keys >= candidate?"); counts are
+  // warp-aggregated, one __syncthreads per round (double-buffered partial sums)
+  uint32_t tau = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = tau | (1u << bit);
+    int cnt = 0;
+    for (int t = tid; t < total; t += SEL_THREADS) cnt += (keys[t] >= cand) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    unsigned* ws = sm->wsum[bit & 1];
+    if (lane == 0) ws[warp] = (unsigned)cnt;
     __syncthreads();
-    const unsigned prefix = sm->sel_prefix;
-    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    for (int t = tid; t < total; t += SEL_THREADS) {
-      const uint32_t x = keys[t];
-      if ((x & himask) == prefix) atomicAdd(&sm->hist[(x >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (warp == 0) {  // bins from the top: find the bin in which the running count reaches `remaining`
-      unsigned mine = 0;
+    unsigned tot = 0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) mine += sm->hist[255 - (lane * 8 + b)];
-      unsigned incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const unsigned remaining = sm->sel_remaining;
-      const unsigned before = incl - mine;
-      const bool here = (before < remaining) && (incl >= remaining);
-      const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
-      if (tot < remaining) {
-        if (lane == 0) {  // fewer keys than NC in this subtree: everything qualifies, tau = smallest
-          sm->sel_remaining = 0;
-          sm->sel_prefix = prefix;  // low bits zero -> all keys with this prefix are >= tau
-        }
-      } else if (here) {
-        unsigned run = before;
-        for (int b = 0; b < 8; ++b) {
-          const int bin = 255 - (lane * 8 + b);
-          const unsigned h = sm->hist[bin];
-          if (run + h >= remaining) {
-            sm->sel_prefix = prefix | ((unsigned)bin << shift);
-            sm->sel_remaining = remaining - run;
-            break;
-          }
-          run += h;
-        }
-      }
-    }
-    __syncthreads();
-    if (sm->sel_remaining == 0) break;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) tot += ws[w];
+    if (tot >= (unsigned)NC) tau = cand;
   }
-  const uint32_t tau = sm->sel_prefix;
-  __syncthreads();
+  // (fewer than NC non-empty keys: tau stays 0 and every non-empty key is a candidate)
 
   // candidates: keys >= tau (non-empty); bounds for the certification: largest key < tau, largest "last slot" key
-  for (int t = tid; t < total; t += SEL_THREADS) {
-    const uint32_t x = keys[t];
-    if (x != 0u && x >= tau) {
-      const unsigned slot = atomicAdd(&sm->n_cand, 1u);
-      if (slot < SEL_CAND_MAX) {
-        const int cta = t / KP;
-        const uint32_t local = low_mask - (x & low_mask);
-        sm->cand_key[slot] = x;
-        sm->cand_row[slot] = (cta + (int)(local >> 7) * G) * tile_n + (int)(local & 127u);
+  {
+    uint32_t below = 0u, mlast = 0u;
+    for (int t = tid; t < total; t += SEL_THREADS) {
+      const uint32_t x = keys[t];
+      if (x != 0u && x >= tau) {
+        const unsigned slot = atomicAdd(&sm->n_cand, 1u);
+        if (slot < SEL_CAND_MAX) {
+          const int cta = t / KP;
+          const uint32_t local = low_mask - (x & low_mask);
+          sm->cand_key[slot] = x;
+          sm->cand_row[slot] = (cta + (int)(local >> 7) * G) * tile_n + (int)(local & 127u);
+        }
+      } else {
+        below = max(below, x);
       }
-    } else if (x != 0u) {
-      atomicMax(&sm->below_max, x);
+      if ((t % KP) == KP - 1) mlast = max(mlast, x);  // a full list may hide rows up to its last key
     }
-    if ((t % KP) == KP - 1) atomicMax(&sm->m_last, x);  // a full list may hide rows up to its last key
+    below = __reduce_max_sync(0xffffffffu, below);
+    mlast = __reduce_max_sync(0xffffffffu, mlast);
+    if (lane == 0) {
+      atomicMax(&sm->below_max, below);
+      atomicMax(&sm->m_last, mlast);
+    }
   }
   __syncthreads();
   const int n_cand = (int)sm->n_cand;
   bool need_rescan = force_rescan != 0 || n_cand > SEL_CAND_MAX;
 
   if (!need_rescan) {
-    for (int f = warp; f < n_cand; f += SEL_THREADS / 32) {
-      const double s = warp_dot_f64(qs, db + (size_t)sm->cand_row[f] * D, D, lane);
-      if (lane == 0) sm->cand_score[f] = s;
+    // float64 re-scoring: each warp takes up to 8 candidates (f = warp + 8 j) and keeps all their loads in flight
+    {
+      constexpr int NW = SEL_THREADS / 32, PER = SEL_CAND_MAX / NW;
+      double acc[PER];
+      const float* rows[PER];
+#pragma unroll
+      for (int jx = 0; jx < PER; ++jx) {
+        const int f = warp + NW * jx;
+        acc[jx] = 0.0;
+        rows[jx] = db + (size_t)sm->cand_row[f < n_cand ? f : 0] * D;
+      }
+      for (int ch = lane; ch < D; ch += 32) {
+        const double qv = (double)qs[ch];
+#pragma unroll
+        for (int jx = 0; jx < PER; ++jx)
+          if (warp + NW * jx < n_cand) acc[jx] = fma(qv, (double)__ldg(rows[jx] + ch), acc[jx]);
+      }
+#pragma unroll
+      for (int jx = 0; jx < PER; ++jx) {
+        const int f = warp + NW * jx;
+        if (f < n_cand) {  // warp-uniform
+          double a = acc[jx];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == 0) sm->cand_score[f] = a;
+        }
+      }
     }
     __syncthreads();
     // rank by (score desc, row asc); the thread holding rank k-1 publishes the k-th best exact score

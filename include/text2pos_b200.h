@@ -185,6 +185,17 @@ typedef struct {
   int32_t hidden;      /* H */
 } t2p_lstm_desc;
 
+/* Host-side tokeniser with the reference's rules (models/modules.py:60-72): '.' and ',' removed, lower-cased, split on
+ * whitespace, out-of-vocabulary words -> 0; rows zero padded to max_tokens.  `texts` holds n_texts NUL-terminated UTF-8
+ * strings back to back (total_bytes including terminators); h_tokens [n_texts, max_tokens] / h_lengths [n_texts] are HOST
+ * buffers (typically the pinned staging buffers of the H2D copy).  ASCII rules only: callers tokenise non-ASCII strings
+ * with the Unicode-aware host language instead. */
+typedef struct t2p_vocab t2p_vocab;
+int t2p_vocab_create(const char* const* words, const int32_t* ids, int n, t2p_vocab** out);
+int t2p_vocab_destroy(t2p_vocab* v);
+int t2p_tokenize(const t2p_vocab* v, const char* texts, size_t total_bytes, int n_texts, int max_tokens, int32_t* h_tokens,
+                 int32_t* h_lengths, int32_t* out_max_len);
+
 size_t t2p_lstm_encode_workspace(int B, int H);
 /* d_tokens [B,T] int32 (row b valid for t < d_lengths[b]), 1 <= lengths <= T.  d_out [B,H] =
  * 0.5*(h_fwd_final + h_bwd_final), L2-normalised per row if normalize != 0. */

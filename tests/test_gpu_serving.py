@@ -1,0 +1,50 @@
+"""GPU: the online engine (strings in, top-k out) -- native tokeniser + staging copies + kernels (+ CUDA graph)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import cpu_state_dict
+from text2pos_cvpr2022_b200 import synthetic as syn
+from text2pos_cvpr2022_b200.serving import OnlineRetrievalEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def test_engine_query_matches_oracle_and_graph_replay(coarse_model):
+    B, N, k = 16, 3000, 10
+    db = syn.synth_db_embeddings(21, N, 256)
+    eng = OnlineRetrievalEngine(coarse_model, db.cuda(), k=k, max_batch=B, max_tokens=64, idx_base=100)
+    texts = syn.synth_queries(5, B)
+    idx, sc = eng.query(texts)
+    idx, sc = idx.copy(), sc.copy()
+    sd = cpu_state_dict(coarse_model)
+    with torch.no_grad():
+        q_ref = oracle.text.encode_text(sd, texts, coarse_model.language_encoder.known_words)
+    # the engine's own text embeddings agree with the oracle to 1e-4 and rank identically on this well separated DB
+    np.testing.assert_allclose(eng.q.cpu().numpy(), q_ref.numpy(), atol=1e-4, rtol=0)
+    ref_i, ref_s = oracle.retrieval.topk(db.numpy(), eng.q.cpu().numpy(), k)
+    np.testing.assert_array_equal(idx - 100, ref_i)
+    np.testing.assert_allclose(sc, ref_s, rtol=1e-12, atol=1e-15)
+    eng.capture("g")
+    idx2, sc2 = eng.query(texts, graph_key="g")
+    np.testing.assert_array_equal(idx2, idx)
+    np.testing.assert_array_equal(sc2, sc)
+    other = syn.synth_queries(6, B)
+    idx3, _ = eng.query(other, graph_key="g")
+    idx4, _ = eng.query(other)
+    np.testing.assert_array_equal(idx3.copy(), idx4)
+    assert eng.stats.cpu().tolist()[1] == 0  # nothing needed the exact rescan
+
+
+def test_engine_unicode_and_errors(coarse_model):
+    db = syn.synth_db_embeddings(22, 500, 256)
+    eng = OnlineRetrievalEngine(coarse_model, db.cuda(), k=5, max_batch=2, max_tokens=32)
+    a = ["The pose is north of a gray building.", "Die Pose ist südlich einer grünen Wand."]  # 2nd: OOV words, non-ASCII
+    idx, _ = eng.query(a)
+    want = coarse_model.encode_text(a)
+    np.testing.assert_allclose(eng.q.cpu().numpy(), want.cpu().numpy(), atol=1e-6, rtol=0)
+    with pytest.raises(ValueError):
+        eng.query(["only one"])
+    with pytest.raises(ValueError):
+        eng.query(["", "x"])

@@ -137,3 +137,29 @@ def test_lstm_register_tiling_is_a_permutation_of_whh():
         for (d, r, i, e, w, kp, jj, g) in [(0, 0, 0, 0, 0, 0, 0, 0), (1, H // 32 - 1, H // 32 - 1, 3, 7, 7, 3, 3), (1, 0, H // 64, 2, 5, 3, 1, 2)]:
             t = w * 32 + kp * 4 + jj
             assert tiled[d, r, i, e, t, g] == whh_t[d, 4 * (8 * i + kp) + e, g * H + 32 * r + 4 * w + jj]
+
+
+def test_native_tokenizer_matches_the_python_rules():
+    """t2p_tokenize (host code of the C ABI) == the reference's rules (models/modules.py:60-72) on ASCII input."""
+    import torch
+
+    from text2pos_cvpr2022_b200 import _lib, synthetic as syn
+    from text2pos_cvpr2022_b200.modules import tokenize
+
+    kw = {w: i + 1 for i, w in enumerate(syn.known_words())}
+    kw["<unk>"] = 0
+    vocab = _lib.Vocab(kw)
+    texts = syn.synth_queries(3, 40) + [
+        "Hello, World.  The POSE\tis north,of a gray building .", "x", ".,.,", "a.b,c d", " lead and trail \n", "north\x1csouth\x0bwest",
+    ]
+    tok = torch.full((len(texts), 70), -7, dtype=torch.int32)
+    ln = torch.zeros(len(texts), dtype=torch.int32)
+    longest = vocab.tokenize_into(texts, tok, ln)
+    rt, rl = tokenize(texts, kw)
+    assert longest == int(rl.max())
+    np.testing.assert_array_equal(ln.numpy(), rl)
+    np.testing.assert_array_equal(tok[:, : rt.shape[1]].numpy(), rt)
+    assert (tok[:, rt.shape[1]:] == 0).all()  # rows are fully written (zero padded)
+    small = torch.zeros(1, 3, dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        vocab.tokenize_into(["one two three four"], small, torch.zeros(1, dtype=torch.int32))

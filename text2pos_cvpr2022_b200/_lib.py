@@ -115,6 +115,9 @@ PROTOTYPES = {
     "t2p_object_embed": (_I, [_P, C.POINTER(ObjEncDesc), _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "t2p_cell_aggregate_workspace": (_SZ, [C.POINTER(CellAggDesc), _I, _I]),
     "t2p_cell_aggregate": (_I, [_P, C.POINTER(CellAggDesc), _P, _P, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "t2p_vocab_create": (_I, [C.POINTER(C.c_char_p), C.POINTER(C.c_int32), _I, C.POINTER(_P)]),
+    "t2p_vocab_destroy": (_I, [_P]),
+    "t2p_tokenize": (_I, [_P, C.c_char_p, _SZ, _I, _I, _P, _P, C.POINTER(C.c_int32)]),
     "t2p_lstm_encode_workspace": (_SZ, [_I, _I]),
     "t2p_lstm_encode": (_I, [_P, C.POINTER(LstmDesc), _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "t2p_superglue_workspace": (_SZ, [_I, _I, _I, _I]),
@@ -201,6 +204,40 @@ class Weights:
         try:
             if getattr(self, "handle", None):
                 load().t2p_weights_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Vocab:
+    """Owns a ``t2p_vocab`` handle: the native tokeniser of the text encoder (``csrc/tokenize.cu``)."""
+
+    def __init__(self, known_words: dict):
+        lib = load()
+        words = [w.encode("utf-8") for w in known_words.keys()]
+        ids = list(known_words.values())
+        n = len(words)
+        arr_w = (C.c_char_p * n)(*words)
+        arr_i = (C.c_int32 * n)(*ids)
+        h = _P()
+        check(lib.t2p_vocab_create(arr_w, arr_i, n, C.byref(h)), "vocab_create")
+        self.handle = h
+
+    def tokenize_into(self, descriptions, h_tokens: torch.Tensor, h_lengths: torch.Tensor) -> int:
+        """Tokenise ASCII ``descriptions`` into the (pinned) int32 host tensors; returns the longest row length."""
+        lib = load()
+        n = len(descriptions)
+        assert h_tokens.dtype == torch.int32 and h_tokens.is_contiguous() and h_tokens.shape[0] >= n and h_lengths.numel() >= n
+        blob = ("\0".join(descriptions) + "\0").encode("utf-8")
+        longest = C.c_int32(0)
+        check(lib.t2p_tokenize(self.handle, blob, len(blob), n, h_tokens.shape[1], h_tokens.data_ptr(), h_lengths.data_ptr(),
+                               C.byref(longest)), "tokenize")
+        return int(longest.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().t2p_vocab_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass

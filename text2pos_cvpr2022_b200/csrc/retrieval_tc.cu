@@ -73,35 +73,52 @@ __global__ void __launch_bounds__(256) row_norm2_max_kernel(const float* __restr
 }
 
 // ---- scan ----------------------------------------------------------------------------------------------
+constexpr int TC_MAX_STAGES = 12;
+
 struct ScanSmem {
   uint64_t q_full;
-  uint64_t full[TC_STAGES];
-  uint64_t empty[TC_STAGES];
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_slot;
 };
 
+struct ScanParams {
+  int B, N, D;
+  int tile_n;      // DB rows per tile (UMMA N), multiple of 16
+  int q_box_rows;  // rows of one query TMA box
+  int db_box_rows; // rows of one DB TMA box (= min(tile_n, N))
+  int q_pitch;     // bytes between the 32-float chunks of the query tile in shared memory (multiple of 1024)
+  int st_pitch;    // bytes per pipeline stage (multiple of 1024)
+  int stages;
+  int nb_bits;     // width of the local-row field of the keys
+  int dup;         // B <= 64: the query tile is loaded twice (TMEM lanes 64..127 mirror 0..63) and the two halves of
+                   // the epilogue warps split the columns of every tile; they write separate key lists (2G sources)
+};
+
 template <int KP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db, int B, int N,
-                        int D, int tile_n, int q_box_rows, int db_box_rows, int nb_bits, uint32_t* __restrict__ part_keys) {
+retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
+                        const ScanParams p, uint32_t* __restrict__ part_keys) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int nch = D >> 5;  // 128-byte chunks along K
+  const int nch = p.D >> 5;  // 128-byte chunks along K
   uint8_t* q_smem = base;
-  uint8_t* st_smem = base + (size_t)nch * TC_CHUNK_BYTES;
-  ScanSmem* sm = reinterpret_cast<ScanSmem*>(st_smem + (size_t)TC_STAGES * TC_CHUNK_BYTES);
+  uint8_t* st_smem = base + (size_t)nch * p.q_pitch;
+  // the UMMA reads 128 rows (16 KB) from every query chunk whatever q_pitch is: 16 KB of slack follow the stages
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(st_smem + (size_t)p.stages * p.st_pitch + 16384);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x;
   const int q0 = blockIdx.y * TC_QM;
-  const int tiles = (N + tile_n - 1) / tile_n;
+  const int tile_n = p.tile_n;
+  const int tiles = (p.N + tile_n - 1) / tile_n;
   const int my_tiles = (tiles - c + G - 1) / G;  // host guarantees c < tiles
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->q_full, 1);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&sm->full[s], 1);
       mbar_init(&sm->empty[s], 1);
     }
@@ -122,17 +139,21 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_db);
-      mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_box_rows * 128));
-      for (int kc = 0; kc < nch; ++kc) tma_load_2d(q_smem + (size_t)kc * TC_CHUNK_BYTES, &tmap_q, kc * 32, q0, &sm->q_full);
+      const int q_copies = p.dup ? 2 : 1;
+      mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_copies * p.q_box_rows * 128));
+      for (int kc = 0; kc < nch; ++kc) {
+        tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_q, kc * 32, q0, &sm->q_full);
+        if (p.dup) tma_load_2d(q_smem + (size_t)kc * p.q_pitch + 64 * 128, &tmap_q, kc * 32, q0, &sm->q_full);
+      }
       int stage = 0;
       uint32_t ph = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
         const int row0 = (c + lt * G) * tile_n;
         for (int kc = 0; kc < nch; ++kc) {
           mbar_wait(&sm->empty[stage], ph ^ 1);
-          mbar_expect_tx(&sm->full[stage], (uint32_t)(db_box_rows * 128));
-          tma_load_2d(st_smem + (size_t)stage * TC_CHUNK_BYTES, &tmap_db, kc * 32, row0, &sm->full[stage]);
-          if (++stage == TC_STAGES) { stage = 0; ph ^= 1; }
+          mbar_expect_tx(&sm->full[stage], (uint32_t)(p.db_box_rows * 128));
+          tma_load_2d(st_smem + (size_t)stage * p.st_pitch, &tmap_db, kc * 32, row0, &sm->full[stage]);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
     }
@@ -153,13 +174,13 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int kc = 0; kc < nch; ++kc) {
           mbar_wait(&sm->full[stage], ph);
           tc_fence_after_sync();
-          const uint64_t a_desc = umma_desc_sw128_kmajor(q_addr + kc * TC_CHUNK_BYTES);
-          const uint64_t b_desc = umma_desc_sw128_kmajor(st_addr + stage * TC_CHUNK_BYTES);
+          const uint64_t a_desc = umma_desc_sw128_kmajor(q_addr + kc * p.q_pitch);
+          const uint64_t b_desc = umma_desc_sw128_kmajor(st_addr + stage * p.st_pitch);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
             umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
           umma_commit(&sm->empty[stage]);
-          if (++stage == TC_STAGES) { stage = 0; ph ^= 1; }
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
         umma_commit(&sm->tmem_full[acc]);
       }
@@ -168,27 +189,31 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   } else {
     // ===== epilogue: TMEM lane = query, columns = DB rows of the tile =====
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-    const int qrow = q0 + quad * 32 + lane;
-    const bool warp_active = (q0 + quad * 32) < B;
-    const uint32_t low_mask = (1u << nb_bits) - 1u;
+    const int tl = quad * 32 + lane;
+    const int half = p.dup ? (tl >> 6) : 0;
+    const int qrow = q0 + (p.dup ? (tl & 63) : tl);
+    const bool warp_active = (q0 + (p.dup ? ((quad & 1) * 32) : quad * 32)) < p.B;
+    const uint32_t low_mask = (1u << p.nb_bits) - 1u;
     uint32_t L[KP];
 #pragma unroll
     for (int i = 0; i < KP; ++i) L[i] = 0u;
-    const int nchunks = (tile_n + 31) >> 5;
+    const int n16 = tile_n >> 4;
+    const int ch_begin = (p.dup && half) ? ((n16 + 1) >> 1) : 0;
+    const int ch_end = (p.dup && !half) ? ((n16 + 1) >> 1) : n16;
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int acc = lt & 1;
       mbar_wait(&sm->tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after_sync();
       if (warp_active) {
         const int row0 = (c + lt * G) * tile_n;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_TILE_MAX + ch * 32, v);
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_TILE_MAX + ch * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = ch * 32 + j;
-            const bool ok = (col < tile_n) && (row0 + col < N);
+          for (int j = 0; j < 16; ++j) {
+            const int col = ch * 16 + j;
+            const bool ok = row0 + col < p.N;
             uint32_t x = ok ? score_to_key(__uint_as_float(v[j]), low_mask, (uint32_t)(lt * TC_TILE_MAX + col)) : 0u;
             if (__any_sync(0xffffffffu, x > L[KP - 1])) {
 #pragma unroll
@@ -204,8 +229,10 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tc_fence_before_sync();
       mbar_arrive(&sm->tmem_empty[acc]);
     }
-    if (qrow < B) {
-      uint4* dst = reinterpret_cast<uint4*>(part_keys + ((size_t)qrow * G + c) * KP);
+    if (qrow < p.B && warp_active) {
+      const int nsrc = p.dup ? 2 * G : G;
+      const int src = p.dup ? 2 * c + half : c;
+      uint4* dst = reinterpret_cast<uint4*>(part_keys + ((size_t)qrow * nsrc + src) * KP);
 #pragma unroll
       for (int i = 0; i < KP / 4; ++i) dst[i] = make_uint4(L[4 * i], L[4 * i + 1], L[4 * i + 2], L[4 * i + 3]);
     }
@@ -226,10 +253,14 @@ __device__ __forceinline__ double warp_dot_f64(const float* __restrict__ q_smem,
   return acc;
 }
 
+constexpr int SEL_SURV_MAX = 256;
+
 struct SelSmem {
   unsigned wsum[2][SEL_THREADS / 32];
-  unsigned n_cand, below_max, m_last, fallback;
+  unsigned n_cand, n_surv, below_max, m_last, fallback, tau0;
   double tk, qq;
+  uint32_t surv_key[SEL_SURV_MAX];
+  int32_t surv_pos[SEL_SURV_MAX];
   uint32_t cand_key[SEL_CAND_MAX];
   int32_t cand_row[SEL_CAND_MAX];
   double cand_score[SEL_CAND_MAX];
@@ -237,81 +268,162 @@ struct SelSmem {
   int64_t wl_i[8][32];
 };
 
+struct SelParams {
+  int B, N, D;
+  int nsrc;    // key lists per query (CTAs of the scan, x2 in dup mode)
+  int G;       // CTAs of the scan (row decoding)
+  int dup;
+  int KP, NC, k, tile_n, nb_bits;
+  int force_rescan;
+  int64_t idx_base;
+};
+
 __global__ void __launch_bounds__(SEL_THREADS)
-retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, int B, int N, int D, int G, int KP, int NC, int k,
-                       int tile_n, int nb_bits, int64_t idx_base, const uint32_t* __restrict__ part_keys,
-                       const float* __restrict__ db_norm2_max, int force_rescan, double* __restrict__ out_s,
-                       int64_t* __restrict__ out_i, int32_t* __restrict__ stats) {
+retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, const SelParams p,
+                       const uint32_t* __restrict__ part_keys, const float* __restrict__ db_norm2_max,
+                       double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats) {
   extern __shared__ __align__(16) uint8_t sel_raw[];
   SelSmem* sm = reinterpret_cast<SelSmem*>(sel_raw);
   float* qs = reinterpret_cast<float*>(sel_raw + sizeof(SelSmem));  // [D]
-  uint32_t* keys = reinterpret_cast<uint32_t*>(qs + D);               // [G*KP]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(qs + p.D);             // [nsrc*KP]
   const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int total = G * KP;
-  const uint32_t low_mask = (1u << nb_bits) - 1u;
+  const int D = p.D, N = p.N, KP = p.KP, NC = p.NC, k = p.k, nsrc = p.nsrc;
+  const int total = nsrc * KP;
+  const uint32_t low_mask = (1u << p.nb_bits) - 1u;
   const double NINF = __longlong_as_double(0xfff0000000000000LL);
+  auto row_of = [&](int pos, uint32_t key) -> int {
+    const int src = pos / KP;
+    const int cta = p.dup ? (src >> 1) : src;
+    const uint32_t local = low_mask - (key & low_mask);
+    return (cta + (int)(local >> 7) * p.G) * p.tile_n + (int)(local & 127u);
+  };
 
-  for (int t = tid; t < D; t += SEL_THREADS) qs[t] = __ldg(q + (size_t)qi * D + t);
   {
-    const uint32_t* src = part_keys + (size_t)qi * total;
-    for (int t = tid; t < total; t += SEL_THREADS) keys[t] = src[t];
+    const uint4* src = reinterpret_cast<const uint4*>(part_keys + (size_t)qi * total);  // KP % 4 == 0, 16-byte aligned
+    uint4* dst = reinterpret_cast<uint4*>(keys);
+    for (int t = tid; t < total / 4; t += SEL_THREADS) dst[t] = __ldg(src + t);
   }
+  for (int t = tid; t < D; t += SEL_THREADS) qs[t] = __ldg(q + (size_t)qi * D + t);
   if (tid == 0) {
     sm->n_cand = 0;
+    sm->n_surv = 0;
     sm->below_max = 0;
     sm->m_last = 0;
     sm->fallback = 0;
-    sm->tk = __longlong_as_double(0xfff0000000000000LL);
+    sm->tau0 = 0;
+    sm->tk = NINF;
     sm->qq = 0.0;
   }
   __syncthreads();
 
-  // tau = NC-th largest key, by bisection on the key bits (32 rounds of "how many keys >= candidate?"); counts are
-  // warp-aggregated, one __syncthreads per round (double-buffered partial sums)
-  uint32_t tau = 0u;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = tau | (1u << bit);
-    int cnt = 0;
-    for (int t = tid; t < total; t += SEL_THREADS) cnt += (keys[t] >= cand) ? 1 : 0;
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    unsigned* ws = sm->wsum[bit & 1];
-    if (lane == 0) ws[warp] = (unsigned)cnt;
-    __syncthreads();
-    unsigned tot = 0;
-#pragma unroll
-    for (int w = 0; w < SEL_THREADS / 32; ++w) tot += ws[w];
-    if (tot >= (unsigned)NC) tau = cand;
-  }
-  // (fewer than NC non-empty keys: tau stays 0 and every non-empty key is a candidate)
-
-  // candidates: keys >= tau (non-empty); bounds for the certification: largest key < tau, largest "last slot" key
+  // a full list may hide rows with keys up to its last entry
   {
-    uint32_t below = 0u, mlast = 0u;
+    uint32_t ml = 0u;
+    for (int t = tid; t < nsrc; t += SEL_THREADS) ml = max(ml, keys[t * KP + KP - 1]);
+    ml = __reduce_max_sync(0xffffffffu, ml);
+    if (lane == 0 && ml) atomicMax(&sm->m_last, ml);
+  }
+
+  // ---- pre-filter: tau0 = NC-th largest list head; at least NC keys are >= tau0, typically only a few more ----------
+  const bool fast = nsrc <= SEL_THREADS && nsrc >= NC;
+  if (fast) {
+    if (tid < nsrc) {
+      const uint32_t mine = keys[tid * KP];
+      int r = 0;
+      for (int j = 0; j < nsrc; ++j) {
+        const uint32_t h = keys[j * KP];
+        r += (h > mine || (h == mine && j < tid)) ? 1 : 0;
+      }
+      if (r == NC - 1) sm->tau0 = mine;
+    }
+    __syncthreads();
+  }
+  const uint32_t tau0 = sm->tau0;  // 0: keep every non-empty key
+  {
+    uint32_t below = 0u;
+    for (int t0 = 0; t0 < total; t0 += SEL_THREADS) {
+      const int t = t0 + tid;
+      const uint32_t x = t < total ? keys[t] : 0u;
+      const bool keep = x != 0u && x >= tau0;
+      if (!keep) below = max(below, x);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        unsigned basev = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) basev = atomicAdd(&sm->n_surv, (unsigned)__popc(m));
+        basev = __shfl_sync(0xffffffffu, basev, leader);
+        const unsigned slot = basev + __popc(m & ((1u << lane) - 1u));
+        if (keep && slot < SEL_SURV_MAX) {
+          sm->surv_key[slot] = x;
+          sm->surv_pos[slot] = t;
+        }
+      }
+    }
+    below = __reduce_max_sync(0xffffffffu, below);
+    if (lane == 0 && below) atomicMax(&sm->below_max, below);
+  }
+  __syncthreads();
+  const int n_surv = (int)sm->n_surv;
+  int n_cand = 0;
+  bool need_rescan = p.force_rescan != 0;
+
+  if (n_surv <= SEL_SURV_MAX) {
+    // exact selection among the survivors by rank counting: rank = #survivors that sort before (key desc, position asc)
+    uint32_t drop = 0u;
+    if (tid < n_surv) {
+      const uint32_t mine = sm->surv_key[tid];
+      const int mpos = sm->surv_pos[tid];
+      int r = 0;
+      for (int j = 0; j < n_surv; ++j) {
+        const uint32_t h = sm->surv_key[j];
+        r += (h > mine || (h == mine && sm->surv_pos[j] < mpos)) ? 1 : 0;
+      }
+      if (r < NC) {
+        sm->cand_key[r] = mine;
+        sm->cand_row[r] = row_of(mpos, mine);
+      } else {
+        drop = mine;
+      }
+    }
+    drop = __reduce_max_sync(0xffffffffu, drop);
+    if (lane == 0 && drop) atomicMax(&sm->below_max, drop);
+    n_cand = min(n_surv, NC);
+  } else {
+    // general path (many sources or dense keys): tau = NC-th largest key by bisection on the key bits
+    uint32_t tau = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = tau | (1u << bit);
+      int cnt = 0;
+      for (int t = tid; t < total; t += SEL_THREADS) cnt += (keys[t] >= cand) ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      unsigned* ws = sm->wsum[bit & 1];
+      if (lane == 0) ws[warp] = (unsigned)cnt;
+      __syncthreads();
+      unsigned tot = 0;
+#pragma unroll
+      for (int w = 0; w < SEL_THREADS / 32; ++w) tot += ws[w];
+      if (tot >= (unsigned)NC) tau = cand;
+    }
+    uint32_t below = 0u;
     for (int t = tid; t < total; t += SEL_THREADS) {
       const uint32_t x = keys[t];
       if (x != 0u && x >= tau) {
         const unsigned slot = atomicAdd(&sm->n_cand, 1u);
         if (slot < SEL_CAND_MAX) {
-          const int cta = t / KP;
-          const uint32_t local = low_mask - (x & low_mask);
           sm->cand_key[slot] = x;
-          sm->cand_row[slot] = (cta + (int)(local >> 7) * G) * tile_n + (int)(local & 127u);
+          sm->cand_row[slot] = row_of(t, x);
         }
       } else {
         below = max(below, x);
       }
-      if ((t % KP) == KP - 1) mlast = max(mlast, x);  // a full list may hide rows up to its last key
     }
     below = __reduce_max_sync(0xffffffffu, below);
-    mlast = __reduce_max_sync(0xffffffffu, mlast);
-    if (lane == 0) {
-      atomicMax(&sm->below_max, below);
-      atomicMax(&sm->m_last, mlast);
-    }
+    if (lane == 0 && below) atomicMax(&sm->below_max, below);
+    __syncthreads();
+    n_cand = (int)sm->n_cand;
+    if (n_cand > SEL_CAND_MAX) need_rescan = true;  // more ties at tau than the candidate buffer holds
   }
   __syncthreads();
-  const int n_cand = (int)sm->n_cand;
-  bool need_rescan = force_rescan != 0 || n_cand > SEL_CAND_MAX;
 
   if (!need_rescan) {
     // float64 re-scoring: each warp takes up to 8 candidates (f = warp + 8 j) and keeps all their loads in flight
@@ -357,7 +469,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
       my_rank = r;
       if (r == k - 1) sm->tk = ms;
     }
-    if (warp == 1) {  // |q|^2 for the error bound
+    if (warp == SEL_THREADS / 32 - 1) {  // |q|^2 for the error bound
       double qq = 0.0;
       for (int ch = lane; ch < D; ch += 32) qq = fma((double)qs[ch], (double)qs[ch], qq);
 #pragma unroll
@@ -386,7 +498,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
     if (!need_rescan) {
       if (tid < n_cand && my_rank < k) {
         out_s[(size_t)qi * k + my_rank] = sm->cand_score[tid];
-        out_i[(size_t)qi * k + my_rank] = idx_base + (int64_t)sm->cand_row[tid];
+        out_i[(size_t)qi * k + my_rank] = p.idx_base + (int64_t)sm->cand_row[tid];
       }
       for (int r = n_cand + tid; r < k; r += SEL_THREADS) {  // N < k: pad
         out_s[(size_t)qi * k + r] = NINF;
@@ -421,7 +533,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
       if (lane < k) {
         const bool ok = top.i != IMAX;
         out_s[(size_t)qi * k + lane] = ok ? top.s : NINF;
-        out_i[(size_t)qi * k + lane] = ok ? idx_base + top.i : (int64_t)-1;
+        out_i[(size_t)qi * k + lane] = ok ? p.idx_base + top.i : (int64_t)-1;
       }
       if (lane == 0 && stats) atomicAdd(stats + 1, 1);
     }
@@ -475,6 +587,7 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
   p.KP = k <= 16 ? 16 : 32;
   p.NC = k <= 16 ? 32 : 48;
   p.qtiles = (B + TC_QM - 1) / TC_QM;
+  p.dup = B <= 64 ? 1 : 0;
   // rows per tile: spread the DB over all SMs when it is small, 128-row tiles otherwise
   int per_sm = (N + sms - 1) / sms;
   p.tile_n = std::min(TC_TILE_MAX, std::max(16, (per_sm + 15) / 16 * 16));
@@ -485,16 +598,25 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
     p.tiles_per_cta = TC_MAX_TILES_PER_CTA;
     p.G = (p.tiles + TC_MAX_TILES_PER_CTA - 1) / TC_MAX_TILES_PER_CTA;
   }
+  p.nsrc = p.dup ? 2 * p.G : p.G;
   p.nb_bits = 7 + ceil_log2(p.tiles_per_cta);
-  p.scan_smem = 1024 + (size_t)(D / 32 + TC_STAGES) * TC_CHUNK_BYTES + sizeof(ScanSmem) + 64;
-  p.sel_smem = sizeof(SelSmem) + (size_t)D * 4 + (size_t)p.G * p.KP * 4;
-  if (p.scan_smem > 227 * 1024 || p.sel_smem > 200 * 1024) return p;
+  const int nch = D / 32;
+  p.q_pitch = (int)align_up((size_t)(p.dup ? 128 : std::min(TC_QM, B)) * 128, 1024);
+  p.st_pitch = p.tile_n * 128;
+  const size_t fixed = 1024 + (size_t)nch * p.q_pitch + 16384 + sizeof(ScanSmem) + 64;
+  const size_t budget = 220 * 1024;
+  if (fixed + 2 * (size_t)p.st_pitch > budget) return p;
+  p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / p.st_pitch);
+  p.stages = std::min(p.stages, std::max(2, nch * p.tiles_per_cta));
+  p.scan_smem = fixed + (size_t)p.stages * p.st_pitch;
+  p.sel_smem = sizeof(SelSmem) + (size_t)D * 4 + (size_t)p.nsrc * p.KP * 4;
+  if (p.sel_smem > 200 * 1024) return p;
   p.ok = true;
   return p;
 }
 
 size_t tc_workspace_bytes(const TcPlan& p, int B) {
-  return align_up((size_t)B * p.G * p.KP * sizeof(uint32_t), 256) + 256 /* norm bound */;
+  return align_up((size_t)B * p.nsrc * p.KP * sizeof(uint32_t), 256) + 256 /* norm bound */;
 }
 
 int launch_row_norm2_max(const float* db, int N, int D, float* out, cudaStream_t s) {
@@ -509,7 +631,7 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
                        const float* d_db_norm2_max, int force_rescan, double* d_out_scores, int64_t* d_out_idx, int32_t* d_stats,
                        void* d_ws, size_t ws_bytes, cudaStream_t s) {
   Arena a(d_ws, ws_bytes);
-  uint32_t* part = a.take<uint32_t>((size_t)B * p.G * p.KP);
+  uint32_t* part = a.take<uint32_t>((size_t)B * p.nsrc * p.KP);
   float* norm_slot = a.take<float>(1);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "retrieve_topk: workspace %zu < %zu bytes", ws_bytes, a.used);
   T2P_REQUIRE((reinterpret_cast<uintptr_t>(d_q) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_db) & 15) == 0, T2P_ERR_INVALID,
@@ -518,23 +640,31 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
     T2P_TRY(launch_row_norm2_max(d_db, N, D, norm_slot, s));
     d_db_norm2_max = norm_slot;
   }
-  const int q_box = std::min(TC_QM, B), db_box = std::min(p.tile_n, N);
+  ScanParams sp;
+  sp.B = B; sp.N = N; sp.D = D;
+  sp.tile_n = p.tile_n;
+  sp.q_box_rows = std::min(p.dup ? 64 : TC_QM, B);
+  sp.db_box_rows = std::min(p.tile_n, N);
+  sp.q_pitch = p.q_pitch; sp.st_pitch = p.st_pitch; sp.stages = p.stages;
+  sp.nb_bits = p.nb_bits; sp.dup = p.dup;
   CUtensorMap tq, tdb;
-  T2P_TRY(make_tmap_rows(&tq, d_q, B, D, q_box));
-  T2P_TRY(make_tmap_rows(&tdb, d_db, N, D, db_box));
+  T2P_TRY(make_tmap_rows(&tq, d_q, B, D, sp.q_box_rows));
+  T2P_TRY(make_tmap_rows(&tdb, d_db, N, D, sp.db_box_rows));
   dim3 grid(p.G, p.qtiles);
   if (p.KP == 16) {
     T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
-    retrieve_scan_tc_kernel<16><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, B, N, D, p.tile_n, q_box, db_box, p.nb_bits, part);
+    retrieve_scan_tc_kernel<16><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, sp, part);
   } else {
     T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
-    retrieve_scan_tc_kernel<32><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, B, N, D, p.tile_n, q_box, db_box, p.nb_bits, part);
+    retrieve_scan_tc_kernel<32><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, sp, part);
   }
   T2P_LAUNCH_CHECK();
+  SelParams q;
+  q.B = B; q.N = N; q.D = D; q.nsrc = p.nsrc; q.G = p.G; q.dup = p.dup; q.KP = p.KP; q.NC = p.NC; q.k = k;
+  q.tile_n = p.tile_n; q.nb_bits = p.nb_bits; q.force_rescan = force_rescan; q.idx_base = idx_base;
   if (p.sel_smem > 48 * 1024)
     T2P_CUDA(cudaFuncSetAttribute(retrieve_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sel_smem));
-  retrieve_select_kernel<<<B, SEL_THREADS, p.sel_smem, s>>>(d_q, d_db, B, N, D, p.G, p.KP, p.NC, k, p.tile_n, p.nb_bits, idx_base, part,
-                                                            d_db_norm2_max, force_rescan, d_out_scores, d_out_idx, d_stats);
+  retrieve_select_kernel<<<B, SEL_THREADS, p.sel_smem, s>>>(d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

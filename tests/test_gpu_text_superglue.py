@@ -36,6 +36,28 @@ def test_language_encoder_vs_oracle(D, B):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("path,B", [(3, 64), (3, 5), (3, 17), (2, 64), (2, 5), (1, 64)])
+def test_language_encoder_every_kernel_path_H256(path, B):
+    """H = 256: 1 = shared-memory cluster kernel, 2 = register-resident kernel, 3 = tcgen05 tensor-core kernel (default)."""
+    enc = LanguageEncoder(syn.known_words(), 256, bi_dir=True)
+    syn.randomize_module_(enc, 77)
+    sd = cpu_state_dict(enc)
+    enc = enc.cuda().eval()
+    texts = syn.synth_queries(300 + B, B, 6)
+    texts[0] = "north"  # length 1
+    if B > 2:
+        texts[2] = "the pose is north of a gray building " * 7  # longest row by far: 56 tokens
+    _, desc = enc.t2p_packed()
+    desc.path = path
+    try:
+        out = enc(texts)
+    finally:
+        desc.path = 0
+    tokens, lengths = oracle.text.tokenize(texts, enc.known_words)
+    ref = oracle.text.language_encoder(sd, "", tokens, lengths)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5, rtol=1e-4)
+
+
 def test_encode_text_normalised(coarse_model):
     texts = syn.synth_queries(5, 64)
     out = coarse_model.encode_text(texts)

@@ -163,3 +163,26 @@ def test_native_tokenizer_matches_the_python_rules():
     small = torch.zeros(1, 3, dtype=torch.int32)
     with pytest.raises(RuntimeError):
         vocab.tokenize_into(["one two three four"], small, torch.zeros(1, dtype=torch.int32))
+
+
+def test_lstm_tensor_core_images_layout_and_split():
+    """packing._lstm_tc_images: fp16 hi/lo split of 2^8*W_hh in the 128-byte-swizzled K-major UMMA layout."""
+    from text2pos_cvpr2022_b200 import packing
+
+    rng = np.random.default_rng(1)
+    H = 256
+    whh_t = rng.uniform(-0.0625, 0.0625, size=(2, H, 4 * H))
+    img = packing._lstm_tc_images(whh_t).view(np.float16).reshape(2, 8, 2, 4, 128, 64)
+    for (d, r, m, k) in [(0, 0, 0, 0), (1, 7, 127, 255), (0, 3, 77, 130), (1, 5, 9, 63), (0, 2, 64, 64)]:
+        unit, gate = m // 4, m % 4
+        w = whh_t[d, k, gate * H + 32 * r + unit] * 256.0
+        chunk, lu, e = k // 64, (k % 64) // 8, k % 8
+        pu = lu ^ (m & 7)
+        hi = float(img[d, r, 0, chunk, m, pu * 8 + e])
+        lo = float(img[d, r, 1, chunk, m, pu * 8 + e])
+        assert hi == float(np.float16(w))
+        assert abs(hi + lo - w) <= 2.0 ** -21 * abs(w) + 1e-12
+    # every weight appears exactly once per part
+    hi_sorted = np.sort(img[:, :, 0].astype(np.float64).reshape(2, -1), axis=1)
+    want = np.sort((whh_t * 256.0).astype(np.float16).astype(np.float64).reshape(2, -1), axis=1)
+    assert np.array_equal(hi_sorted, want)

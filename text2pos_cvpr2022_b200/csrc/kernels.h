@@ -49,4 +49,9 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
                        const float* d_db_norm2_max, int force_rescan, double* d_out_scores, int64_t* d_out_idx, int32_t* d_stats,
                        void* d_ws, size_t ws_bytes, cudaStream_t s);
 
+
+// tensor-core LSTM recurrence (H = 256), csrc/lstm_tc.cu
+int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,
+                   float* hfinal, cudaStream_t s);
+
 }  // namespace t2p

@@ -551,7 +551,22 @@ int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32
               T2P_ERR_INVALID, "lstm_encode: descriptor outside the weight blob");
   cudaStream_t s = as_stream(stream);
   const float* xproj = wptr(w, desc->xproj_off);
-  if (desc->whh_reg_off >= 0 && (H == 32 || H == 64 || H == 128 || H == 256)) {
+  T2P_REQUIRE(desc->path >= 0 && desc->path <= 3, T2P_ERR_INVALID, "lstm_encode: path=%d outside [0,3]", desc->path);
+  const bool tc_ok = H == 256 && desc->whh_tc_off >= 0 && desc->xproj4_off >= 0;
+  T2P_REQUIRE(desc->path != 3 || tc_ok, T2P_ERR_UNSUPPORTED, "lstm_encode: the tensor-core path needs H == 256 and its packed weights");
+  if (tc_ok && (desc->path == 0 || desc->path == 3)) {
+    T2P_REQUIRE((size_t)desc->whh_tc_off + (size_t)2 * 8 * 32768 <= w->n_floats &&
+                    (size_t)desc->xproj4_off + (size_t)2 * V * 4 * H <= w->n_floats,
+                T2P_ERR_INVALID, "lstm_encode: tensor-core weights outside the blob");
+    Arena a(d_ws, ws_bytes);
+    float* hfinal = a.take<float>((size_t)2 * B * H);
+    T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "lstm_encode: workspace %zu < %zu bytes", ws_bytes, a.used);
+    T2P_TRY(launch_lstm_tc(wptr(w, desc->xproj4_off), wptr(w, desc->whh_tc_off), d_tokens, d_lengths, B, T, V, hfinal, s));
+    lstm_finalize_kernel<<<(B + 7) / 8, 256, 0, s>>>(hfinal, B, H, normalize, d_out);
+    T2P_LAUNCH_CHECK();
+    return T2P_OK;
+  }
+  if (desc->whh_reg_off >= 0 && (H == 32 || H == 64 || H == 128 || H == 256) && desc->path != 1) {
     T2P_REQUIRE((size_t)desc->whh_reg_off + (size_t)2 * H * 4 * H <= w->n_floats, T2P_ERR_INVALID,
                 "lstm_encode: whh_reg outside the weight blob");
     Arena a(d_ws, ws_bytes);

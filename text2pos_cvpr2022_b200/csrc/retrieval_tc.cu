@@ -255,7 +255,7 @@ __device__ __forceinline__ double warp_dot_f64(const float* __restrict__ q_smem,
 
 constexpr int SEL_SURV_MAX = 256;
 
-struct SelSmem {
+struct __align__(16) SelSmem {
   unsigned wsum[2][SEL_THREADS / 32];
   unsigned n_cand, n_surv, below_max, m_last, fallback, tau0;
   double tk, qq;

@@ -33,12 +33,21 @@ class BlobBuilder:
         self.n = 0
 
     def add(self, arr: np.ndarray) -> int:
-        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        """float64 values, rounded to float32 once, here."""
+        return self._append(np.ascontiguousarray(arr, dtype=np.float64).reshape(-1).astype(np.float32))
+
+    def add_raw_u32(self, arr: np.ndarray) -> int:
+        """raw 32-bit words (e.g. packed fp16 pairs) stored bit-exactly inside the float32 blob."""
+        a = np.ascontiguousarray(arr).reshape(-1)
+        assert a.dtype == np.uint32
+        return self._append(a.view(np.float32))
+
+    def _append(self, a: np.ndarray) -> int:
         off = self.n
         pad = (-a.size) % self.ALIGN
         self.chunks.append(a)
         if pad:
-            self.chunks.append(np.zeros(pad))
+            self.chunks.append(np.zeros(pad, dtype=np.float32))
         self.n += a.size + pad
         return off
 
@@ -58,8 +67,8 @@ class BlobBuilder:
         return d
 
     def finish(self) -> torch.Tensor:
-        blob = np.concatenate(self.chunks) if self.chunks else np.zeros(1)
-        return torch.from_numpy(blob.astype(np.float32))
+        blob = np.concatenate(self.chunks) if self.chunks else np.zeros(1, dtype=np.float32)
+        return torch.from_numpy(blob)
 
 
 def _bn(sd, prefix) -> Optional[Dict[str, np.ndarray]]:
@@ -135,8 +144,41 @@ def pack_lstm(bb: BlobBuilder, sd, prefix: str) -> _lib.LstmDesc:
     d.xproj_off = bb.add(np.stack(xproj))
     d.whh_off = bb.add(np.stack(whh))
     d.whh_reg_off = bb.add(_lstm_register_tiling(np.stack(whh))) if H in (32, 64, 128, 256) else -1
+    if H == 256:
+        xp = np.stack(xproj)  # [2, V, 4H], columns g*H + u
+        d.xproj4_off = bb.add(xp.reshape(2, V, 4, H).transpose(0, 1, 3, 2))  # [2, V, H, 4]
+        d.whh_tc_off = bb.add_raw_u32(_lstm_tc_images(np.stack(whh)))
+    else:
+        d.xproj4_off = d.whh_tc_off = -1
     d.vocab, d.hidden = V, H
+    d.path = 0
     return d
+
+
+LSTM_TC_WSCALE = 256.0  # 2^8: keeps the fp16 "lo" halves of the weights out of the subnormal range
+
+
+def _lstm_tc_images(whh_t: np.ndarray) -> np.ndarray:
+    """whh_t [2, 256, 1024] (= W_hh^T) -> uint32 words of the shared-memory images read by ``lstm_tc_kernel``:
+    [dir 2][cluster rank 8][hi|lo 2][K chunk 4][row m 128][64 fp16], row m = 4*unit + gate of the rank's 32 hidden units,
+    value = fp16 split of 2^8 * W_hh[gate*H + 32 r + unit][k], and the eight 16-byte units of every 128-byte row stored at
+    position (unit index XOR (m & 7)) -- the 128-byte swizzle of a K-major UMMA operand."""
+    H = whh_t.shape[1]
+    assert H == 256
+    m = np.arange(128)
+    unit, gate = m // 4, m % 4
+    out = np.zeros((2, 8, 2, 4, 128, 8, 8), dtype=np.float16)  # [..., row, 16-byte unit, element]
+    swz = np.arange(8)[None, :] ^ (m[:, None] & 7)              # physical unit v holds logical unit v ^ (m & 7)
+    for d in range(2):
+        for r in range(8):
+            cols = gate * H + 32 * r + unit                    # [128]
+            w = whh_t[d][:, cols].T * LSTM_TC_WSCALE            # [128 rows, 256 k]
+            hi = w.astype(np.float16)
+            lo = (w - hi.astype(np.float64)).astype(np.float16)
+            for part, mat in enumerate((hi, lo)):
+                t = mat.reshape(128, 4, 8, 8).transpose(1, 0, 2, 3)  # [chunk, row, logical unit, elem]
+                out[d, r, part] = np.take_along_axis(t, swz[None, :, :, None], axis=2)
+    return out.reshape(-1).view(np.uint32)
 
 
 def _lstm_register_tiling(whh_t: np.ndarray) -> np.ndarray:

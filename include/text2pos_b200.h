@@ -182,9 +182,9 @@ typedef struct {
                           [2, H/32 (cluster rank r), H/32 (i), 4 (e), 256 (thread), 4 (gate g)] with
                           thread = w*32 + kp*4 + jj  ->  W_hh[dir][g*H + 32 r + 4 w + jj][4*(8 i + kp) + e] */
   int64_t xproj4_off;  /* H == 256 only, else -1: [2, V, H, 4] = xproj with the 4 gates of a unit contiguous */
-  int64_t whh_tc_off;  /* H == 256 only, else -1: shared-memory images of the fp16 hi/lo split of 2^8 * W_hh for the
-                          tensor-core kernel (csrc/lstm_tc.cu): [2, 8 (cluster rank), 2 (hi|lo), 4 (K chunk), 128 (row
-                          m = 4*unit + gate), 64 fp16 with the 16-byte units of a row XOR-swizzled by (m & 7)] */
+  int64_t whh_tc_off;  /* H == 256 only, else -1: tensor-memory images of the fp16 hi/lo split of 2^8 * W_hh for the
+                          tensor-core kernel (csrc/lstm_tc.cu): [2, 8 (cluster rank), 2 (hi|lo), 32 (k-unit), 128 (row
+                          m = 4*unit + gate), 8 fp16 (k = 8*k-unit + e)] */
   int32_t vocab;       /* V (index 0 = <unk>/padding) */
   int32_t hidden;      /* H */
   int32_t path;        /* 0 = auto (tensor-core kernel when H == 256, else register kernel, else cluster kernel);

@@ -1,18 +1,22 @@
 // (a6) text encoder recurrence on the tcgen05 tensor cores (H = 256).
 //
 // Cluster of 8 CTAs per (direction, group of 16 sequences); CTA rank r owns hidden units [32r, 32r+32), i.e. 128
-// gate columns, whose slice of W_hh stays in shared memory for the whole sequence as an fp16 hi/lo pair
-// (W*2^8 = hi + lo, relative error 2^-22; host-tiled K-major, 128-byte swizzle, loaded with cp.async.bulk).
-// The hidden state lives in shared memory of every CTA as the UMMA B operand [16 sequences x 256] fp16 hi/lo
-// (h*2^4 = hi + lo), double buffered.  One step:
-//   control warp : wait for h_{t-1} (mbarrier transaction count), fence.proxy.async, issue 48 tcgen05.mma
-//                  kind::f16 (M = 128 gate columns, N = 16 sequences, K = 16; products hi*hi + hi*lo + lo*hi,
-//                  fp32 accumulation in TMEM), commit to an mbarrier;
-//   4 epilogue warps (TMEM lane = gate column, rows ordered unit-major so that 4 consecutive lanes hold the gates
-//                  i,f,g,o of one unit): tcgen05.ld, 4x4 lane transpose (each thread then owns one unit for 4
-//                  sequences), + input projection (per-token table, L2), cell update in registers, h -> fp16 hi/lo,
-//                  staged through 512 bytes of shared memory per warp into 16-byte chunks of the swizzled B layout,
-//                  one st.async per chunk and peer CTA that completes bytes on the peer's h mbarrier.
+// gate columns (UMMA M), whose slice of W_hh lives in TENSOR MEMORY for the whole sequence as an fp16 hi/lo pair
+// (W*2^8 = hi + lo, relative error 2^-22): 2 x 128 TMEM columns (two fp16 per 32-bit column), written once with
+// tcgen05.st.  The A operand therefore never touches shared memory again (the SS form re-read 192 KB of weights per
+// step, ~1500 cycles of shared-memory bandwidth).  The hidden state lives in shared memory of every CTA as the UMMA B
+// operand [16 sequences x 256] fp16 hi/lo (h*2^4 = hi + lo; K-major, 128-byte swizzle), double buffered.  One step:
+//   control warp : wait for h_{t-1} (mbarrier transaction count), fence.proxy.async, one elected lane issues 48
+//                  tcgen05.mma kind::f16 (M = 128 gate columns, N = 16 sequences, K = 16; products hi*hi + hi*lo +
+//                  lo*hi, fp32 accumulation in TMEM), commit to an mbarrier.  The loop runs warp-uniformly so that the
+//                  descriptors stay in uniform registers;
+//   8 epilogue warps (warp w: TMEM lane quadrant w%4, sequences 8*(w/4)..+7; TMEM lane = gate column, rows ordered
+//                  unit-major so that 4 consecutive lanes hold the gates i,f,g,o of one unit): tcgen05.ld, 4x4 block
+//                  transpose over the 4 lanes of a unit (two butterfly stages of predicated selects + shuffles; each
+//                  thread then owns one unit for 2 sequences), + input projection (per-token table, L2), cell update in
+//                  registers with MUFU-only activations, h -> fp16 hi/lo, staged through 256 bytes of shared memory
+//                  per warp into 16-byte chunks of the swizzled B layout, one st.async per chunk and peer CTA that
+//                  completes bytes on the peer's h mbarrier.
 // No cluster barrier, no __syncthreads and no fence sits on the step.  Dropping the lo*lo product and the fp16
 // rounding of lo bound the relative error of a product by ~3*2^-22: fp32-grade results (tests: 1e-4 vs the oracle).
 #include <cooperative_groups.h>
@@ -30,15 +34,17 @@ using namespace sm100;
 constexpr int LTC_H = 256;
 constexpr int LTC_CS = 8;        // CTAs per cluster
 constexpr int LTC_NS = 16;       // sequences per cluster (UMMA N)
-constexpr int LTC_THREADS = 160; // warps 0-3: epilogue (TMEM quadrants 0-3), warp 4: control
-constexpr int LTC_W_BYTES = 2 * 4 * 128 * 128;  // hi|lo x 4 K-chunks x 128 rows x 128 bytes = 128 KB
+constexpr int LTC_EPI_WARPS = 8;
+constexpr int LTC_THREADS = 32 * (LTC_EPI_WARPS + 1);  // warps 0-7: epilogue, warp 8: control
+constexpr int LTC_W_HALFS = 2 * 128 * 256;      // per (direction, rank): hi|lo x 128 rows x 256 k fp16 = 128 KB
 constexpr int LTC_HB_PART = 4 * LTC_NS * 128;   // one of {hi, lo}: 4 K-chunks x 16 rows x 128 bytes = 8 KB
 constexpr int LTC_HB_BUF = 2 * LTC_HB_PART;     // hi + lo
+constexpr int LTC_TMEM_COLS = 512;              // [0,128) W hi, [128,256) W lo, [256,272) accumulator
+constexpr int LTC_D_COL = 256;
 constexpr float LTC_UNSCALE = 1.f / 4096.f;     // 2^-8 (W) * 2^-4 (h)
 constexpr float LTC_HSCALE = 16.f;
 
 struct LtcBars {
-  uint64_t w_bar;
   uint64_t h_bar[2];
   uint64_t mma_bar;
   uint32_t tmem_slot;
@@ -48,17 +54,40 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   // fp16 A/B (format 0), fp32 accumulate, both K-major
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ bool ltc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -72,20 +101,33 @@ __device__ __forceinline__ void ltc_st_async_v4(uint32_t remote_addr, uint4 v, u
                ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
                : "memory");
 }
-__device__ __forceinline__ float ltc_sigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
-__device__ __forceinline__ float ltc_tanh(float x) { return fmaf(-2.f, __frcp_rn(1.f + __expf(2.f * x)), 1.f); }
+// MUFU-only activations (ex2.approx + rcp.approx, ~2 ulp each, no slow-path branches): absolute error ~2e-7
+__device__ __forceinline__ float ltc_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ltc_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ltc_sigmoid(float x) { return ltc_rcp(1.f + ltc_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float ltc_tanh(float x) { return fmaf(-2.f, ltc_rcp(1.f + ltc_ex2(2.885390081777927f * x)), 1.f); }
 
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates (i,f,g,o) of (token, unit)
-               const uint4* __restrict__ w_img,     // [2][CS][LTC_W_BYTES / 16] shared-memory image of the W_hh slice
+               const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (LTC_W_HALFS per slice)
                const int32_t* __restrict__ tokens, const int32_t* __restrict__ lengths, int B, int T, int V,
                float* __restrict__ hfinal) {
-  extern __shared__ uint8_t ltc_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ltc_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_smem = base;                                    // [hi: 4 x 16 KB][lo: 4 x 16 KB]
-  uint8_t* hb_smem = base + LTC_W_BYTES;                     // [2 buffers][hi|lo][4 chunks][16 x 128 B]
-  uint8_t* stage_smem = hb_smem + 2 * LTC_HB_BUF;            // [4 warps][hi|lo][16 seqs][8 units] fp16 = 512 B each
-  LtcBars* bars = reinterpret_cast<LtcBars*>(stage_smem + 4 * 512);
+  // declared 1024-byte aligned (128-byte swizzle atoms): keeps the shared address space visible to the compiler, so the
+  // token / staging accesses compile to LDS/STS instead of generic loads
+  extern __shared__ __align__(1024) uint8_t ltc_raw[];
+  uint8_t* base = ltc_raw;
+  if ((smem_u32(base) & 1023u) != 0u) __trap();
+  uint8_t* hb_smem = base;                                   // [2 buffers][hi|lo][4 chunks][16 x 128 B]
+  uint8_t* stage_smem = hb_smem + 2 * LTC_HB_BUF;            // [8 warps][hi|lo][8 seqs][8 units] fp16 = 256 B each
+  LtcBars* bars = reinterpret_cast<LtcBars*>(stage_smem + LTC_EPI_WARPS * 256);
   int* tok = reinterpret_cast<int*>(bars + 1);               // [NS][T]
   int* len = tok + LTC_NS * T;                               // [NS]
 
@@ -106,7 +148,6 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   }
   if (tid < LTC_NS) len[tid] = (b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
   if (tid == 0) {
-    mbar_init(&bars->w_bar, 1);
     mbar_init(&bars->h_bar[0], 1);
     mbar_init(&bars->h_bar[1], 1);
     mbar_init(&bars->mma_bar, 1);
@@ -114,7 +155,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     mbar_expect_tx(&bars->h_bar[0], STEP_BYTES);  // armed for their first use (steps 2 and 1)
     mbar_expect_tx(&bars->h_bar[1], STEP_BYTES);
   }
-  if (warp == 4) tmem_alloc<32>(&bars->tmem_slot);
+  if (warp == LTC_EPI_WARPS) tmem_alloc<LTC_TMEM_COLS>(&bars->tmem_slot);
   fence_proxy_async_smem();  // the zero-filled h buffers (generic stores) will be read by the tensor core
   tc_fence_before_sync();
   __syncthreads();
@@ -123,156 +164,182 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   int max_len = 0;
 #pragma unroll
   for (int b = 0; b < LTC_NS; ++b) max_len = max(max_len, len[b]);
+
+  if (warp < LTC_EPI_WARPS) {
+    // W_hh slice -> tensor memory: thread = row m (TMEM lane 32*(warp%4) + lane), warps 0-3 write the hi part, 4-7 the lo
+    // part; element k of the row sits in the (k%2) half of 32-bit column k/2.  Coalesced: [k-unit][row] x 16 bytes.
+    const int q = warp & 3, part = warp >> 2;
+    const uint4* src = w_img + ((size_t)(dir * LTC_CS + rank) * 2 + part) * (32 * 128) + (q * 32 + lane);
+#pragma unroll 1
+    for (int grp = 0; grp < 4; ++grp) {  // 32 columns = 64 k values = 8 k-units per tcgen05.st
+      uint32_t v[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 x = __ldg(src + (size_t)(grp * 8 + j) * 128);
+        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+      }
+      tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + part * 128 + grp * 32, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // barriers + zeroed buffers visible cluster-wide
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-  if (warp == 4) {
-    // ===== control warp: W load, then per step wait(h) -> MMAs -> commit =====
-    if (lane == 0) {
-      mbar_expect_tx(&bars->w_bar, LTC_W_BYTES);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)(dir * LTC_CS + rank) * LTC_W_BYTES;
-      for (int pc = 0; pc < LTC_W_BYTES / 16384; ++pc) bulk_load(w_smem + pc * 16384, src + pc * 16384, 16384, &bars->w_bar);
-      mbar_wait(&bars->w_bar, 0);
-      const uint32_t idesc = umma_idesc_f16(128, LTC_NS);
-      const uint32_t w_addr = smem_u32(w_smem), hb_addr = smem_u32(hb_smem);
-      for (int step = 0; step < max_len; ++step) {
-        const int cur = step & 1;
-        if (step > 0) {
-          mbar_wait(&bars->h_bar[cur], (uint32_t)(((step - 1) >> 1) & 1));
-          mbar_expect_tx(&bars->h_bar[cur], STEP_BYTES);  // re-arm for step + 2
-        }
-        fence_proxy_async_smem();  // h was written through the generic proxy (st.async), the UMMA reads via the async proxy
-        tc_fence_after_sync();
+  if (warp == LTC_EPI_WARPS) {
+    // ===== control warp (warp-uniform loop; one elected lane issues): per step wait(h) -> MMAs -> commit =====
+    const uint32_t idesc = umma_idesc_f16(128, LTC_NS);
+    const uint32_t hb_addr = smem_u32(hb_smem);
+    const uint32_t tmem_d = tmem_base + LTC_D_COL;
+    for (int step = 0; step < max_len; ++step) {
+      const int cur = step & 1;
+      if (step > 0) {
+        mbar_wait(&bars->h_bar[cur], (uint32_t)(((step - 1) >> 1) & 1));
+        if (lane == 0) mbar_expect_tx(&bars->h_bar[cur], STEP_BYTES);  // re-arm for step + 2
+      }
+      fence_proxy_async_smem();  // h was written through the generic proxy (st.async), the UMMA reads via the async proxy
+      tc_fence_after_sync();
+      if (ltc_elect_one()) {
         const uint32_t hb = hb_addr + cur * LTC_HB_BUF;
         bool acc = false;
 #pragma unroll
         for (int prod = 0; prod < 3; ++prod) {  // W_hi*h_hi, W_hi*h_lo, W_lo*h_hi
-          const uint32_t wa = w_addr + (prod == 2 ? LTC_W_BYTES / 2 : 0);
+          const uint32_t a_col = tmem_base + (prod == 2 ? 128 : 0);
           const uint32_t ha = hb + (prod == 1 ? LTC_HB_PART : 0);
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc) {
-            const uint64_t a_desc = umma_desc_sw128_kmajor(wa + kc * 16384);
             const uint64_t b_desc = umma_desc_sw128_kmajor(ha + kc * (LTC_NS * 128));
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {  // K = 16 fp16 = 32 bytes per instruction
-              umma_f16_ss(tmem_base, a_desc + 2 * ks, b_desc + 2 * ks, idesc, acc);
+            for (int ks = 0; ks < 4; ++ks) {  // K = 16 fp16 per instruction: 8 TMEM columns of A, 32 bytes of B
+              umma_f16_ts(tmem_d, a_col + (kc * 4 + ks) * 8, b_desc + 2 * ks, idesc, acc);
               acc = true;
             }
           }
         }
         umma_commit(&bars->mma_bar);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ===== epilogue warps: TMEM lane m = 32*warp + lane  <->  unit 8*warp + lane/4, gate lane%4 =====
+    // ===== epilogue warps: TMEM lane m = 32*q + lane  <->  unit 8*q + lane/4, gate lane%4; columns = sequences =====
+    const int q = warp & 3, hf = warp >> 2;
     const int g = lane & 3, jj = lane >> 2;
-    const int unit = u0 + 8 * warp + jj;
-    int my_len[4];
+    const bool gb0 = (g & 1) != 0, gb1 = (g & 2) != 0;
+    const int unit = u0 + 8 * q + jj;
+    const int s0 = 8 * hf + 2 * g;  // this thread finalises sequences s0, s0 + 1 of the group
+    int my_len[2];
 #pragma unroll
-    for (int sq = 0; sq < 4; ++sq) my_len[sq] = len[4 * g + sq];
-    float c_state[4] = {0.f, 0.f, 0.f, 0.f}, h_state[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < 2; ++e) my_len[e] = len[s0 + e];
+    float c_state[2] = {0.f, 0.f}, h_state[2] = {0.f, 0.f};
     const float4* xp_base = xproj4 + (size_t)dir * V * LTC_H + unit;
-    auto token_at = [&](int sq, int step) -> int {
-      const int L = my_len[sq];
+    auto token_at = [&](int e, int step) -> int {
+      const int L = my_len[e];
       if (step >= L) return 0;
-      return tok[(4 * g + sq) * T + (dir ? (L - 1 - step) : step)];
+      return tok[(s0 + e) * T + (dir ? (L - 1 - step) : step)];
     };
-    float4 xn[4];
+    float4 xn[2];
 #pragma unroll
-    for (int sq = 0; sq < 4; ++sq) xn[sq] = __ldg(xp_base + (size_t)token_at(sq, 0) * LTC_H);
-    // staging: this warp's [hi|lo][16 seqs][8 units] fp16; lane l later ships chunk (part = l/16, seq = l%16)
-    __half* stage = reinterpret_cast<__half*>(stage_smem + warp * 512);
-    const int ship_part = lane >> 4, ship_seq = lane & 15;
-    // destination of that chunk inside a B buffer: K index k0 = u0 + 8*warp, chunk k0/64, 16-byte unit (k0%64)/8 ^ (seq&7)
-    const int k0 = u0 + 8 * warp;
+    for (int e = 0; e < 2; ++e) xn[e] = __ldg(xp_base + (size_t)token_at(e, 0) * LTC_H);
+    // staging: this warp's [hi|lo][8 seqs][8 units] fp16; lane l ships chunk (part = (l%16)/8, seq = 8*hf + l%8) to the
+    // four CTAs 4*(l/16) .. +3
+    __half* stage = reinterpret_cast<__half*>(stage_smem + warp * 256);
+    const int ship_part = (lane >> 3) & 1, ship_sl = lane & 7, ship_seq = 8 * hf + ship_sl, ship_r0 = (lane >> 4) * 4;
+    // destination of that chunk inside a B buffer: K index k0 = u0 + 8*q, chunk k0/64, 16-byte unit (k0%64)/8 ^ (seq&7)
+    const int k0 = u0 + 8 * q;
     const uint32_t ship_off = (uint32_t)(ship_part * LTC_HB_PART + (k0 >> 6) * (LTC_NS * 128) + ship_seq * 128 +
                                          ((((k0 & 63) >> 3) ^ (ship_seq & 7)) << 4));
-    const uint32_t hb_addr = smem_u32(hb_smem), hbar_addr = smem_u32(&bars->h_bar[0]);
+    // cluster-mapped addresses of this lane's chunk slot (buffer 0) and of h_bar[0] in its four destination CTAs
+    uint32_t rdst[4], rbar[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      rdst[r] = ltc_map_rank(smem_u32(hb_smem) + ship_off, (uint32_t)(ship_r0 + r));
+      rbar[r] = ltc_map_rank(smem_u32(&bars->h_bar[0]), (uint32_t)(ship_r0 + r));
+    }
+    const uint32_t tmem_src = tmem_base + ((uint32_t)(q * 32) << 16) + LTC_D_COL + 8 * hf;
 
     for (int step = 0; step < max_len; ++step) {
       const int nxt = (step + 1) & 1;
-      float4 xg[4];
+      float4 xg[2];
 #pragma unroll
-      for (int sq = 0; sq < 4; ++sq) xg[sq] = xn[sq];
+      for (int e = 0; e < 2; ++e) xg[e] = xn[e];
       if (step + 1 < max_len) {
 #pragma unroll
-        for (int sq = 0; sq < 4; ++sq) xn[sq] = __ldg(xp_base + (size_t)token_at(sq, step + 1) * LTC_H);
+        for (int e = 0; e < 2; ++e) xn[e] = __ldg(xp_base + (size_t)token_at(e, step + 1) * LTC_H);
       }
       mbar_wait(&bars->mma_bar, (uint32_t)(step & 1));
       tc_fence_after_sync();
-      uint32_t v[16];
-      tmem_ld_32x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+      uint32_t v[8];
+      tmem_ld_32x8(tmem_src, v);
       tmem_ld_wait();
       tc_fence_before_sync();
-      // 4x4 transpose over the 4 lanes of a unit: afterwards pre[sq][g'] = gate g' of sequence 4g+sq
-      float pre[4][4];
+      // 4x4 block transpose (blocks of 2 sequences) over the 4 lanes of a unit as two butterfly stages (xor 2, xor 1);
+      // every register index is static and every choice a predicated select, so the warp never diverges.  Lane g ends
+      // up with, for its sequences: kk0 = gate g, r0 = gate g^1, kk1 = gate g^2, r1 = gate g^3.
+      float ka[4], ra[4];
 #pragma unroll
-      for (int sq = 0; sq < 4; ++sq) {
-        const float own = __uint_as_float(g == 0 ? v[sq] : g == 1 ? v[4 + sq] : g == 2 ? v[8 + sq] : v[12 + sq]);
-#pragma unroll
-        for (int gp = 0; gp < 4; ++gp) pre[sq][gp] = own;  // slot gp == g keeps it; the others are overwritten below
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t keep = gb1 ? v[4 + i] : v[i];
+        const uint32_t send = gb1 ? v[i] : v[4 + i];
+        ka[i] = __uint_as_float(keep);
+        ra[i] = __uint_as_float(__shfl_xor_sync(0xffffffffu, send, 2));
       }
 #pragma unroll
-      for (int r = 1; r < 4; ++r) {
-        const int pg = g ^ r;  // partner's gate index = the block of sequences the partner owns
-#pragma unroll
-        for (int sq = 0; sq < 4; ++sq) {
-          const uint32_t send = pg == 0 ? v[sq] : pg == 1 ? v[4 + sq] : pg == 2 ? v[8 + sq] : v[12 + sq];
-          const float got = __uint_as_float(__shfl_xor_sync(0xffffffffu, send, r));  // partner's gate pg for my sequences
-#pragma unroll
-          for (int gp = 0; gp < 4; ++gp)
-            if (gp == pg) pre[sq][gp] = got;
-        }
-      }
-      // cell update for (unit, sequences 4g..4g+3)
-#pragma unroll
-      for (int sq = 0; sq < 4; ++sq) {
-        const float pi = fmaf(pre[sq][0], LTC_UNSCALE, xg[sq].x);
-        const float pf = fmaf(pre[sq][1], LTC_UNSCALE, xg[sq].y);
-        const float pg_ = fmaf(pre[sq][2], LTC_UNSCALE, xg[sq].z);
-        const float po = fmaf(pre[sq][3], LTC_UNSCALE, xg[sq].w);
+      for (int e = 0; e < 2; ++e) {
+        const float kk0 = gb0 ? ka[2 + e] : ka[e];
+        const float sa = gb0 ? ka[e] : ka[2 + e];
+        const float kk1 = gb0 ? ra[2 + e] : ra[e];
+        const float sb = gb0 ? ra[e] : ra[2 + e];
+        const float r0 = __shfl_xor_sync(0xffffffffu, sa, 1);
+        const float r1 = __shfl_xor_sync(0xffffffffu, sb, 1);
+        const float x = gb0 ? r0 : kk0, y = gb0 ? kk0 : r0, z = gb0 ? r1 : kk1, w = gb0 ? kk1 : r1;
+        const float pre_i = gb1 ? z : x, pre_g = gb1 ? x : z, pre_f = gb1 ? w : y, pre_o = gb1 ? y : w;
+        // cell update for (unit, sequence s0 + e)
+        const float pi = fmaf(pre_i, LTC_UNSCALE, xg[e].x);
+        const float pf = fmaf(pre_f, LTC_UNSCALE, xg[e].y);
+        const float pg_ = fmaf(pre_g, LTC_UNSCALE, xg[e].z);
+        const float po = fmaf(pre_o, LTC_UNSCALE, xg[e].w);
         const float ig = ltc_sigmoid(pi), fg = ltc_sigmoid(pf), gg = ltc_tanh(pg_), og = ltc_sigmoid(po);
-        const float cn = fmaf(fg, c_state[sq], ig * gg);
+        const float cn = fmaf(fg, c_state[e], ig * gg);
         const float hn = og * ltc_tanh(cn);
-        const bool active = step < my_len[sq];
-        c_state[sq] = active ? cn : c_state[sq];
-        h_state[sq] = active ? hn : h_state[sq];
+        const bool active = step < my_len[e];
+        c_state[e] = active ? cn : c_state[e];
+        h_state[e] = active ? hn : h_state[e];
       }
       if (step + 1 < max_len) {
-        // h*2^4 -> fp16 hi/lo, staged as [part][seq][unit-in-warp]
+        // h*2^4 -> fp16 hi/lo, staged as [part][seq-in-half][unit-in-warp]
 #pragma unroll
-        for (int sq = 0; sq < 4; ++sq) {
-          const float hs = h_state[sq] * LTC_HSCALE;
+        for (int e = 0; e < 2; ++e) {
+          const float hs = h_state[e] * LTC_HSCALE;
           const __half hi = __float2half_rn(hs);
           const __half lo = __float2half_rn(hs - __half2float(hi));
-          stage[(0 * LTC_NS + 4 * g + sq) * 8 + jj] = hi;
-          stage[(1 * LTC_NS + 4 * g + sq) * 8 + jj] = lo;
+          stage[(0 * 8 + 2 * g + e) * 8 + jj] = hi;
+          stage[(1 * 8 + 2 * g + e) * 8 + jj] = lo;
         }
         __syncwarp();
-        const uint4 chunk = *reinterpret_cast<const uint4*>(stage + (ship_part * LTC_NS + ship_seq) * 8);
+        const uint4 chunk = *reinterpret_cast<const uint4*>(stage + (ship_part * 8 + ship_sl) * 8);
         __syncwarp();  // the staging area is rewritten next step
-        const uint32_t dst = hb_addr + (uint32_t)nxt * LTC_HB_BUF + ship_off;
-        const uint32_t dbar = hbar_addr + (uint32_t)nxt * 8u;
+        const uint32_t doff = (uint32_t)nxt * LTC_HB_BUF, boff = (uint32_t)nxt * 8u;
 #pragma unroll
-        for (int r = 0; r < LTC_CS; ++r) ltc_st_async_v4(ltc_map_rank(dst, r), chunk, ltc_map_rank(dbar, r));
+        for (int r = 0; r < 4; ++r) ltc_st_async_v4(rdst[r] + doff, chunk, rbar[r] + boff);
       }
     }
 #pragma unroll
-    for (int sq = 0; sq < 4; ++sq) {
-      const int b = b0 + 4 * g + sq;
-      if (b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[sq];
+    for (int e = 0; e < 2; ++e) {
+      const int b = b0 + s0 + e;
+      if (b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[e];
     }
   }
   tc_fence_before_sync();
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // no CTA exits while a peer may still store into it
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after_sync();
-  if (warp == 4) tmem_dealloc<32>(tmem_base);
+  if (warp == LTC_EPI_WARPS) tmem_dealloc<LTC_TMEM_COLS>(tmem_base);
 }
 
 size_t lstm_tc_smem_bytes(int T) {
-  return 1024 + (size_t)LTC_W_BYTES + 2 * LTC_HB_BUF + 4 * 512 + sizeof(LtcBars) + ((size_t)LTC_NS * T + LTC_NS) * sizeof(int) + 64;
+  return (size_t)2 * LTC_HB_BUF + LTC_EPI_WARPS * 256 + sizeof(LtcBars) + ((size_t)LTC_NS * T + LTC_NS) * sizeof(int) + 64;
 }
 
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,

@@ -159,16 +159,15 @@ LSTM_TC_WSCALE = 256.0  # 2^8: keeps the fp16 "lo" halves of the weights out of 
 
 
 def _lstm_tc_images(whh_t: np.ndarray) -> np.ndarray:
-    """whh_t [2, 256, 1024] (= W_hh^T) -> uint32 words of the shared-memory images read by ``lstm_tc_kernel``:
-    [dir 2][cluster rank 8][hi|lo 2][K chunk 4][row m 128][64 fp16], row m = 4*unit + gate of the rank's 32 hidden units,
-    value = fp16 split of 2^8 * W_hh[gate*H + 32 r + unit][k], and the eight 16-byte units of every 128-byte row stored at
-    position (unit index XOR (m & 7)) -- the 128-byte swizzle of a K-major UMMA operand."""
+    """whh_t [2, 256, 1024] (= W_hh^T) -> uint32 words of the tensor-memory images loaded by ``lstm_tc_kernel``:
+    [dir 2][cluster rank 8][hi|lo 2][k-unit 32][row m 128][8 fp16], row m = 4*unit + gate of the rank's 32 hidden units,
+    value = fp16 split of 2^8 * W_hh[gate*H + 32 r + unit][8*ku + e].  A warp reads 32 consecutive rows of one k-unit
+    (512 contiguous bytes); the 8 fp16 of a row are 4 TMEM columns (element k in the (k%2) half of column k/2)."""
     H = whh_t.shape[1]
     assert H == 256
     m = np.arange(128)
     unit, gate = m // 4, m % 4
-    out = np.zeros((2, 8, 2, 4, 128, 8, 8), dtype=np.float16)  # [..., row, 16-byte unit, element]
-    swz = np.arange(8)[None, :] ^ (m[:, None] & 7)              # physical unit v holds logical unit v ^ (m & 7)
+    out = np.zeros((2, 8, 2, 32, 128, 8), dtype=np.float16)
     for d in range(2):
         for r in range(8):
             cols = gate * H + 32 * r + unit                    # [128]
@@ -176,8 +175,7 @@ def _lstm_tc_images(whh_t: np.ndarray) -> np.ndarray:
             hi = w.astype(np.float16)
             lo = (w - hi.astype(np.float64)).astype(np.float16)
             for part, mat in enumerate((hi, lo)):
-                t = mat.reshape(128, 4, 8, 8).transpose(1, 0, 2, 3)  # [chunk, row, logical unit, elem]
-                out[d, r, part] = np.take_along_axis(t, swz[None, :, :, None], axis=2)
+                out[d, r, part] = mat.reshape(128, 32, 8).transpose(1, 0, 2)
     return out.reshape(-1).view(np.uint32)
 
 

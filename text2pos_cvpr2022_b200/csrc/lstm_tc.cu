@@ -1,6 +1,6 @@
 // (a6) text encoder recurrence on the tcgen05 tensor cores (H = 256).
 //
-// Cluster of 8 CTAs per (direction, group of 16 sequences); CTA rank r owns hidden units [32r, 32r+32), i.e. 128
+// Cluster of 8 CTAs per (direction, group of <= 16 sequences); CTA rank r owns hidden units [32r, 32r+32), i.e. 128
 // gate columns (UMMA M), whose slice of W_hh lives in TENSOR MEMORY for the whole sequence as an fp16 hi/lo pair
 // (W*2^8 = hi + lo, relative error 2^-22): 2 x 128 TMEM columns (two fp16 per 32-bit column), written once with
 // tcgen05.st.  The A operand therefore never touches shared memory again (the SS form re-read 192 KB of weights per
@@ -21,6 +21,7 @@
 // rounding of lo bound the relative error of a product by ~3*2^-22: fp32-grade results (tests: 1e-4 vs the oracle).
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "sm100.cuh"
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates (i,f,g,o) of (token, unit)
                const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (LTC_W_HALFS per slice)
                const int32_t* __restrict__ tokens, const int32_t* __restrict__ lengths, int B, int T, int V,
-               float* __restrict__ hfinal) {
+               float* __restrict__ hfinal, int ns) {
   // declared 1024-byte aligned (128-byte swizzle atoms): keeps the shared address space visible to the compiler, so the
   // token / staging accesses compile to LDS/STS instead of generic loads
   extern __shared__ __align__(1024) uint8_t ltc_raw[];
@@ -136,17 +137,17 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   const int cid = blockIdx.x / LTC_CS;
   const int dir = cid & 1, group = cid >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = group * LTC_NS;
+  const int b0 = group * ns;  // the group's sequences are b0 .. b0 + ns - 1 (ns <= 16; UMMA columns >= ns are padding)
   const int u0 = rank * 32;
-  constexpr uint32_t STEP_BYTES = LTC_HB_BUF;  // 16 KB of h (hi + lo, 16 sequences x 256 units) per step
+  const uint32_t STEP_BYTES = (uint32_t)ns * 1024u;  // h of the group's ns real sequences: 256 units x (hi + lo) fp16 each
 
   for (int t = tid; t < 2 * LTC_HB_BUF / 16; t += LTC_THREADS) reinterpret_cast<uint4*>(hb_smem)[t] = make_uint4(0, 0, 0, 0);
   for (int t = tid; t < LTC_NS * T; t += LTC_THREADS) {
     const int b = t / T, tt = t - b * T;
-    const int v = (b0 + b < B) ? tokens[(size_t)(b0 + b) * T + tt] : 0;
+    const int v = (b < ns && b0 + b < B) ? tokens[(size_t)(b0 + b) * T + tt] : 0;
     tok[t] = (v < 0 || v >= V) ? 0 : v;
   }
-  if (tid < LTC_NS) len[tid] = (b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
+  if (tid < LTC_NS) len[tid] = (tid < ns && b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
   if (tid == 0) {
     mbar_init(&bars->h_bar[0], 1);
     mbar_init(&bars->h_bar[1], 1);
@@ -189,7 +190,9 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
   if (warp == LTC_EPI_WARPS) {
-    // ===== control warp (warp-uniform loop; one elected lane issues): per step wait(h) -> MMAs -> commit =====
+    // ===== control warp (warp-uniform loop; one elected lane issues): per step wait(h) -> MMAs -> commit.  One barrier
+    // per buffer: splitting it per source CTA to start the MMAs of early slices sooner was measured SLOWER (8 waits +
+    // 8 proxy fences per step cost more than the 48 MMAs they would hide). =====
     const uint32_t idesc = umma_idesc_f16(128, LTC_NS);
     const uint32_t hb_addr = smem_u32(hb_smem);
     const uint32_t tmem_d = tmem_base + LTC_D_COL;
@@ -198,8 +201,8 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
       if (step > 0) {
         mbar_wait(&bars->h_bar[cur], (uint32_t)(((step - 1) >> 1) & 1));
         if (lane == 0) mbar_expect_tx(&bars->h_bar[cur], STEP_BYTES);  // re-arm for step + 2
+        fence_proxy_async_smem();  // h arrived through the generic proxy (st.async), the UMMA reads via the async proxy
       }
-      fence_proxy_async_smem();  // h was written through the generic proxy (st.async), the UMMA reads via the async proxy
       tc_fence_after_sync();
       if (ltc_elect_one()) {
         const uint32_t hb = hb_addr + cur * LTC_HB_BUF;
@@ -242,10 +245,10 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     float4 xn[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) xn[e] = __ldg(xp_base + (size_t)token_at(e, 0) * LTC_H);
-    // staging: this warp's [hi|lo][8 seqs][8 units] fp16; lane l ships chunk (part = (l%16)/8, seq = 8*hf + l%8) to the
-    // four CTAs 4*(l/16) .. +3
+    // staging: this warp's [hi|lo][8 seqs][8 units] fp16; lane l ships chunk (part = (l%16)/8, seq = 8*hf + l%8) to four
+    // CTAs: lanes 0-15 to rank+1..rank+4, lanes 16-31 to rank, rank+5..rank+7 (no two CTAs target the same peer at once)
     __half* stage = reinterpret_cast<__half*>(stage_smem + warp * 256);
-    const int ship_part = (lane >> 3) & 1, ship_sl = lane & 7, ship_seq = 8 * hf + ship_sl, ship_r0 = (lane >> 4) * 4;
+    const int ship_part = (lane >> 3) & 1, ship_sl = lane & 7, ship_seq = 8 * hf + ship_sl;
     // destination of that chunk inside a B buffer: K index k0 = u0 + 8*q, chunk k0/64, 16-byte unit (k0%64)/8 ^ (seq&7)
     const int k0 = u0 + 8 * q;
     const uint32_t ship_off = (uint32_t)(ship_part * LTC_HB_PART + (k0 >> 6) * (LTC_NS * 128) + ship_seq * 128 +
@@ -254,8 +257,9 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     uint32_t rdst[4], rbar[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      rdst[r] = ltc_map_rank(smem_u32(hb_smem) + ship_off, (uint32_t)(ship_r0 + r));
-      rbar[r] = ltc_map_rank(smem_u32(&bars->h_bar[0]), (uint32_t)(ship_r0 + r));
+      const int dst_rank = (lane < 16) ? (rank + 1 + r) : (r == 0 ? rank : rank + 4 + r);
+      rdst[r] = ltc_map_rank(smem_u32(hb_smem) + ship_off, (uint32_t)(dst_rank & (LTC_CS - 1)));
+      rbar[r] = ltc_map_rank(smem_u32(&bars->h_bar[0]), (uint32_t)(dst_rank & (LTC_CS - 1)));
     }
     const uint32_t tmem_src = tmem_base + ((uint32_t)(q * 32) << 16) + LTC_D_COL + 8 * hf;
 
@@ -322,13 +326,16 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
         __syncwarp();  // the staging area is rewritten next step
         const uint32_t doff = (uint32_t)nxt * LTC_HB_BUF, boff = (uint32_t)nxt * 8u;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) ltc_st_async_v4(rdst[r] + doff, chunk, rbar[r] + boff);
+        if (ship_seq < ns) {  // rows of padding sequences stay zero
+#pragma unroll
+          for (int r = 0; r < 4; ++r) ltc_st_async_v4(rdst[r] + doff, chunk, rbar[r] + boff);
+        }
       }
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int b = b0 + s0 + e;
-      if (b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[e];
+      if (s0 + e < ns && b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[e];
     }
   }
   tc_fence_before_sync();
@@ -347,7 +354,19 @@ int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* token
   const size_t smem = lstm_tc_smem_bytes(T);
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "lstm_encode: T=%d needs %zu bytes of shared memory", T, smem);
   T2P_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int groups = (B + LTC_NS - 1) / LTC_NS;
+  // The step is bound by the SM-to-SM network (every CTA sends and receives 7/8 KB per sequence of its group), so the
+  // batch is spread over as many clusters as B200 co-schedules: at most 15 clusters of 8 CTAs are resident
+  // (launch__cluster_max_active), i.e. 7 groups x 2 directions; larger batches run 16 sequences per cluster in waves.
+  int groups, ns;
+  if (B <= 7 * LTC_NS) {
+    const int gmax = getenv("T2P_LSTM_GROUPS") ? atoi(getenv("T2P_LSTM_GROUPS")) : 7;
+    groups = B < gmax ? B : gmax;
+    ns = (B + groups - 1) / groups;
+    groups = (B + ns - 1) / ns;
+  } else {
+    ns = LTC_NS;
+    groups = (B + LTC_NS - 1) / LTC_NS;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * 2 * LTC_CS);
   cfg.blockDim = dim3(LTC_THREADS);
@@ -361,7 +380,7 @@ int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* token
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   T2P_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc_kernel, reinterpret_cast<const float4*>(xproj4), reinterpret_cast<const uint4*>(w_img),
-                              tokens, lengths, B, T, V, hfinal));
+                              tokens, lengths, B, T, V, hfinal, ns));
   return T2P_OK;
 }
 

@@ -48,3 +48,36 @@ def test_engine_unicode_and_errors(coarse_model):
         eng.query(["only one"])
     with pytest.raises(ValueError):
         eng.query(["", "x"])
+
+
+def test_engine_pipelined_submit_collect_equals_query(coarse_model):
+    """depth-2 engine: results of submit()/collect() with two batches in flight equal the synchronous query()."""
+    B, N, k = 8, 2000, 10
+    db = syn.synth_db_embeddings(23, N, 256).cuda()
+    ref = OnlineRetrievalEngine(coarse_model, db, k=k, max_batch=B, max_tokens=64)
+    eng = OnlineRetrievalEngine(coarse_model, db, k=k, max_batch=B, max_tokens=64, depth=2)
+    eng.capture_all("g")
+    batches = [syn.synth_queries(30 + i, B) for i in range(5)]
+    want = []
+    for b in batches:
+        i, s = ref.query(b)
+        want.append((i.copy(), s.copy()))
+    got = []
+    for n, b in enumerate(batches):
+        if len(eng._inflight) == 2:
+            i, s = eng.collect()
+            got.append((i.copy(), s.copy()))
+        eng.submit(b, graph_key="g" if n % 2 else None)
+    while eng._inflight:
+        i, s = eng.collect()
+        got.append((i.copy(), s.copy()))
+    assert len(got) == len(want)
+    for (gi, gs), (wi, ws) in zip(got, want):
+        np.testing.assert_array_equal(gi, wi)
+        np.testing.assert_array_equal(gs, ws)
+    with pytest.raises(RuntimeError):
+        eng.submit(batches[0]), eng.submit(batches[1]), eng.submit(batches[2])
+    while eng._inflight:
+        eng.collect()
+    i0, _ = eng.query(batches[0])  # the synchronous call still works on a pipelined engine
+    np.testing.assert_array_equal(i0, want[0][0])

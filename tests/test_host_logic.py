@@ -166,20 +166,19 @@ def test_native_tokenizer_matches_the_python_rules():
 
 
 def test_lstm_tensor_core_images_layout_and_split():
-    """packing._lstm_tc_images: fp16 hi/lo split of 2^8*W_hh in the 128-byte-swizzled K-major UMMA layout."""
+    """packing._lstm_tc_images: fp16 hi/lo split of 2^8*W_hh in the tensor-memory load order [k-unit][row][8 fp16]."""
     from text2pos_cvpr2022_b200 import packing
 
     rng = np.random.default_rng(1)
     H = 256
     whh_t = rng.uniform(-0.0625, 0.0625, size=(2, H, 4 * H))
-    img = packing._lstm_tc_images(whh_t).view(np.float16).reshape(2, 8, 2, 4, 128, 64)
+    img = packing._lstm_tc_images(whh_t).view(np.float16).reshape(2, 8, 2, 32, 128, 8)
     for (d, r, m, k) in [(0, 0, 0, 0), (1, 7, 127, 255), (0, 3, 77, 130), (1, 5, 9, 63), (0, 2, 64, 64)]:
         unit, gate = m // 4, m % 4
         w = whh_t[d, k, gate * H + 32 * r + unit] * 256.0
-        chunk, lu, e = k // 64, (k % 64) // 8, k % 8
-        pu = lu ^ (m & 7)
-        hi = float(img[d, r, 0, chunk, m, pu * 8 + e])
-        lo = float(img[d, r, 1, chunk, m, pu * 8 + e])
+        ku, e = k // 8, k % 8
+        hi = float(img[d, r, 0, ku, m, e])
+        lo = float(img[d, r, 1, ku, m, e])
         assert hi == float(np.float16(w))
         assert abs(hi + lo - w) <= 2.0 ** -21 * abs(w) + 1e-12
     # every weight appears exactly once per part

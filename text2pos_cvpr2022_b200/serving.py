@@ -1,10 +1,15 @@
 """Online coarse retrieval engine: tokens -> text embedding -> top-k cell indices against a resident DB.
 
 This is the fast path ``bench.py`` measures: all device buffers are preallocated, the four kernels of one step
-(cluster LSTM, finalize, partial top-k, merge) are enqueued through the C ABI with no per-step allocation, and the
+(tensor-core LSTM, finalize, top-k scan, select) are enqueued through the C ABI with no per-step allocation, and the
 step can be captured once into a CUDA graph and replayed.  ``query(strings)`` is the end-to-end user call: host
 tokenisation, pinned staging, H2D, step, D2H.
+
+The engine owns ``depth`` independent *slots* (staging buffers, workspaces, a stream and CUDA graphs each).  With
+``depth >= 2``, ``submit()`` / ``collect()`` keep several batches in flight: the host tokenises batch i+1 while the
+GPU works on batch i, and the top-k of batch i overlaps the text encoder of batch i+1 on the idle SMs.
 """
+import collections
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -14,25 +19,11 @@ from . import _lib
 from .modules import tokenize
 
 
-class OnlineRetrievalEngine:
-    KERNELS_PER_STEP = 4  # lstm_reg, lstm_finalize, retrieve_scan_tc, retrieve_select
+class _Slot:
+    """One in-flight batch: staging buffers both ways, the text embedding, workspaces, a stream and its graphs."""
 
-    def __init__(self, model, db: torch.Tensor, k: int = 10, max_batch: int = 64, max_tokens: int = 64,
-                 idx_base: int = 0, cell_ids: Optional[Sequence[str]] = None):
-        self.lib = _lib.load()
-        self.model = model
-        self.weights, desc = model.t2p_packed()
-        self.lstm_desc = desc["lstm"] if isinstance(desc, dict) else desc
-        self.device = model.t2p_device()
-        self.k, self.B, self.T = int(k), int(max_batch), int(max_tokens)
-        self.D = self.lstm_desc.hidden
-        self.idx_base = int(idx_base)
-        self.cell_ids = None if cell_ids is None else np.asarray(cell_ids)
-        self.known_words = model.language_encoder.known_words if hasattr(model, "language_encoder") else model.known_words
-        self.vocab = _lib.Vocab(self.known_words)
-        self.set_db(db)
-        dev = self.device
-        B, T, k = self.B, self.T, self.k
+    def __init__(self, eng: "OnlineRetrievalEngine", own_stream: bool):
+        dev, B, T, k, D = eng.device, eng.B, eng.T, eng.k, eng.D
         # one staging buffer each way: [tokens B*T | lengths B] int32 in, [scores B*k f64 | idx B*k i64] out
         self.d_in = torch.zeros(B * T + B, dtype=torch.int32, device=dev)
         self.d_in[B * T:] = 1
@@ -48,10 +39,46 @@ class OnlineRetrievalEngine:
         self.out_idx = self.d_out[B * k:].view(B, k)
         self.h_scores = self.h_out[: B * k].view(torch.float64).view(B, k)
         self.h_idx = self.h_out[B * k:].view(B, k)
-        self.q = torch.empty(B, self.D, dtype=torch.float32, device=dev)
+        self.q = torch.empty(B, D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            self.ws_lstm = torch.empty(max(256, self.lib.t2p_lstm_encode_workspace(B, self.D)), dtype=torch.uint8, device=dev)
-        self._graphs = {}
+            self.ws_lstm = torch.empty(max(256, eng.lib.t2p_lstm_encode_workspace(B, D)), dtype=torch.uint8, device=dev)
+            self.stream = torch.cuda.Stream() if own_stream else None
+            self.done = torch.cuda.Event()
+        self.ws_topk = None
+        self.graphs = {}
+
+
+class OnlineRetrievalEngine:
+    KERNELS_PER_STEP = 4  # lstm_tc, lstm_finalize, retrieve_scan_tc, retrieve_select
+
+    def __init__(self, model, db: torch.Tensor, k: int = 10, max_batch: int = 64, max_tokens: int = 64,
+                 idx_base: int = 0, cell_ids: Optional[Sequence[str]] = None, depth: int = 1):
+        self.lib = _lib.load()
+        self.model = model
+        self.weights, desc = model.t2p_packed()
+        self.lstm_desc = desc["lstm"] if isinstance(desc, dict) else desc
+        self.device = model.t2p_device()
+        self.k, self.B, self.T = int(k), int(max_batch), int(max_tokens)
+        self.D = self.lstm_desc.hidden
+        self.idx_base = int(idx_base)
+        self.cell_ids = None if cell_ids is None else np.asarray(cell_ids)
+        self.known_words = model.language_encoder.known_words if hasattr(model, "language_encoder") else model.known_words
+        self.vocab = _lib.Vocab(self.known_words)
+        self.depth = max(1, int(depth))
+        # slot 0 runs on the caller's current stream (query / enqueue_*); further slots own a stream each
+        self.slots = [_Slot(self, own_stream=(i > 0 or self.depth > 1)) for i in range(self.depth)]
+        self._inflight = collections.deque()
+        self._next = 0
+        self.set_db(db)
+
+    # slot 0 under the historical attribute names
+    def __getattr__(self, name):
+        if name in ("d_in", "h_in", "tokens", "lengths", "h_tokens", "h_lengths", "d_out", "h_out", "out_scores", "out_idx",
+                    "h_scores", "h_idx", "q", "ws_lstm", "ws_topk"):
+            return getattr(self.__dict__["slots"][0], name)
+        if name == "_graphs":
+            return self.__dict__["slots"][0].graphs
+        raise AttributeError(name)
 
     def set_db(self, db: torch.Tensor):
         from .retrieval import db_row_norm2_max
@@ -62,69 +89,77 @@ class OnlineRetrievalEngine:
         self.stats = torch.zeros(2, dtype=torch.int32, device=self.device)  # [certified, rescanned] query counters
         with torch.cuda.device(self.device):
             n = self.lib.t2p_retrieve_topk_workspace(self.B, self.db.shape[0], self.db.shape[1], self.k)
-            self.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=self.device)
-        self._graphs = {}
+            for s in self.slots:
+                s.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=self.device)
+                s.graphs = {}
 
     # ---- one step on the current stream ---------------------------------------------------------------------------
-    def enqueue_encode(self, tokens: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None):
-        tokens = self.tokens if tokens is None else tokens
-        lengths = self.lengths if lengths is None else lengths
+    def enqueue_encode(self, tokens: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None, slot: int = 0):
+        s = self.slots[slot]
+        tokens = s.tokens if tokens is None else tokens
+        lengths = s.lengths if lengths is None else lengths
         _lib.check(
             self.lib.t2p_lstm_encode(self.weights.handle, self.lstm_desc, tokens.data_ptr(), lengths.data_ptr(),
-                                     self.B, tokens.shape[1], 1, self.q.data_ptr(), self.ws_lstm.data_ptr(), self.ws_lstm.numel(),
+                                     self.B, tokens.shape[1], 1, s.q.data_ptr(), s.ws_lstm.data_ptr(), s.ws_lstm.numel(),
                                      _lib.stream_ptr(self.device)),
             "lstm_encode",
         )
 
-    def enqueue_topk(self, db: Optional[torch.Tensor] = None):
+    def enqueue_topk(self, db: Optional[torch.Tensor] = None, slot: int = 0):
         """``db``: an alternative resident copy with the SAME rows (hence the same norm bound) as ``self.db``."""
+        s = self.slots[slot]
         db = self.db if db is None else db
         _lib.check(
-            self.lib.t2p_retrieve_topk_ex(self.q.data_ptr(), db.data_ptr(), self.B, db.shape[0], db.shape[1], self.k,
-                                          self.idx_base, self.db_norm2_max.data_ptr(), 0, self.out_scores.data_ptr(),
-                                          self.out_idx.data_ptr(), self.stats.data_ptr(), self.ws_topk.data_ptr(),
-                                          self.ws_topk.numel(), _lib.stream_ptr(self.device)),
+            self.lib.t2p_retrieve_topk_ex(s.q.data_ptr(), db.data_ptr(), self.B, db.shape[0], db.shape[1], self.k,
+                                          self.idx_base, self.db_norm2_max.data_ptr(), 0, s.out_scores.data_ptr(),
+                                          s.out_idx.data_ptr(), self.stats.data_ptr(), s.ws_topk.data_ptr(),
+                                          s.ws_topk.numel(), _lib.stream_ptr(self.device)),
             "retrieve_topk",
         )
 
-    def enqueue_step(self, db: Optional[torch.Tensor] = None):
-        self.enqueue_encode()
-        self.enqueue_topk(db)
+    def enqueue_step(self, db: Optional[torch.Tensor] = None, slot: int = 0):
+        self.enqueue_encode(slot=slot)
+        self.enqueue_topk(db, slot=slot)
 
-    def capture(self, key=0, db: Optional[torch.Tensor] = None):
-        """Capture one step (staging buffers -> top-k against ``db``) into a CUDA graph stored under ``key``."""
+    def capture(self, key=0, db: Optional[torch.Tensor] = None, slot: int = 0):
+        """Capture one step (staging buffers of ``slot`` -> top-k against ``db``) into a CUDA graph stored under ``key``."""
         with torch.cuda.device(self.device):
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self.enqueue_step(db)  # warm-up outside capture (cudaFuncSetAttribute etc.)
+                self.enqueue_step(db, slot=slot)  # warm-up outside capture (cudaFuncSetAttribute etc.)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.enqueue_step(db)
-            self._graphs[key] = g
+                self.enqueue_step(db, slot=slot)
+            self.slots[slot].graphs[key] = g
         return g
 
-    def replay(self, key=0):
-        self._graphs[key].replay()
+    def capture_all(self, key=0, db: Optional[torch.Tensor] = None):
+        for i in range(self.depth):
+            self.capture(key, db, slot=i)
 
-    # ---- end-to-end user call -------------------------------------------------------------------------------------
-    def stage_queries(self, descriptions: Sequence[str]):
+    def replay(self, key=0, slot: int = 0):
+        self.slots[slot].graphs[key].replay()
+
+    # ---- end-to-end user calls ------------------------------------------------------------------------------------
+    def stage_queries(self, descriptions: Sequence[str], slot: int = 0):
         """Host tokenisation straight into the pinned staging buffer (native tokeniser; Unicode strings take the
         Python one, whose lower()/split() are Unicode-aware)."""
+        s = self.slots[slot]
         if len(descriptions) != self.B:
             raise ValueError(f"engine built for batches of {self.B} queries, got {len(descriptions)}")
         if all(d.isascii() for d in descriptions):
-            self.vocab.tokenize_into(descriptions, self.h_tokens, self.h_lengths)
+            self.vocab.tokenize_into(descriptions, s.h_tokens, s.h_lengths)
         else:
             tokens, lengths = tokenize(descriptions, self.known_words)
             if tokens.shape[1] > self.T:
                 raise ValueError(f"engine built for <= {self.T} tokens per query, got {tokens.shape[1]}")
-            self.h_tokens.zero_()
-            self.h_tokens[:, : tokens.shape[1]] = torch.from_numpy(tokens)
-            self.h_lengths[:] = torch.from_numpy(lengths)
-        if int(self.h_lengths.min()) < 1:
+            s.h_tokens.zero_()
+            s.h_tokens[:, : tokens.shape[1]] = torch.from_numpy(tokens)
+            s.h_lengths[:] = torch.from_numpy(lengths)
+        if int(s.h_lengths.min()) < 1:
             raise ValueError("empty description (the reference's packed LSTM rejects length 0 too)")
 
     def load_tokens(self, tokens: np.ndarray, lengths: np.ndarray):
@@ -136,18 +171,54 @@ class OnlineRetrievalEngine:
         self.h_lengths[:] = torch.from_numpy(lengths)
         self.d_in.copy_(self.h_in, non_blocking=True)
 
-    def query(self, descriptions: List[str], graph_key=None):
-        """strings -> (idx [B,k] int64 numpy, scores [B,k] float64 numpy); synchronous.
-        One pinned H2D copy, the four kernels (a captured CUDA graph if ``graph_key`` names one), one D2H copy."""
-        self.stage_queries(descriptions)
-        self.d_in.copy_(self.h_in, non_blocking=True)
-        if graph_key is not None and graph_key in self._graphs:
-            self._graphs[graph_key].replay()
+    def _enqueue_query(self, s: _Slot, slot: int, graph_key):
+        s.d_in.copy_(s.h_in, non_blocking=True)
+        if graph_key is not None and graph_key in s.graphs:
+            s.graphs[graph_key].replay()
         else:
-            self.enqueue_step()
-        self.h_out.copy_(self.d_out, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self.h_idx.numpy(), self.h_scores.numpy()
+            self.enqueue_step(slot=slot)
+        s.h_out.copy_(s.d_out, non_blocking=True)
+
+    def query(self, descriptions: List[str], graph_key=None):
+        """strings -> (idx [B,k] int64 numpy, scores [B,k] float64 numpy); synchronous, slot 0.
+        One pinned H2D copy, the four kernels (a captured CUDA graph if ``graph_key`` names one), one D2H copy."""
+        if self._inflight:
+            raise RuntimeError("query() while submitted batches are in flight: collect() them first")
+        s = self.slots[0]
+        self.stage_queries(descriptions, 0)
+        if s.stream is not None:
+            with torch.cuda.stream(s.stream):
+                self._enqueue_query(s, 0, graph_key)
+            s.stream.synchronize()
+        else:
+            self._enqueue_query(s, 0, graph_key)
+            torch.cuda.current_stream(self.device).synchronize()
+        return s.h_idx.numpy(), s.h_scores.numpy()
+
+    def submit(self, descriptions: List[str], graph_key=None) -> int:
+        """Asynchronous ``query``: tokenises into the next free slot, enqueues H2D + step + D2H on the slot's stream and
+        returns the slot number.  At most ``depth`` batches may be in flight; results come back in order via ``collect``."""
+        if self.depth < 2:
+            raise RuntimeError("submit() needs an engine built with depth >= 2")
+        if len(self._inflight) >= self.depth:
+            raise RuntimeError(f"{self.depth} batches already in flight: collect() first")
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        s = self.slots[slot]
+        self.stage_queries(descriptions, slot)
+        with torch.cuda.stream(s.stream):
+            self._enqueue_query(s, slot, graph_key)
+            s.done.record()
+        self._inflight.append(slot)
+        return slot
+
+    def collect(self):
+        """Result of the oldest submitted batch: (idx, scores) numpy views of its pinned buffers, valid until the slot
+        is submitted again."""
+        slot = self._inflight.popleft()
+        s = self.slots[slot]
+        s.done.synchronize()
+        return s.h_idx.numpy(), s.h_scores.numpy()
 
     def h2d_bytes(self) -> int:
         return self.h_in.numel() * 4

@@ -203,6 +203,21 @@ int t2p_vocab_destroy(t2p_vocab* v);
 int t2p_tokenize(const t2p_vocab* v, const char* texts, size_t total_bytes, int n_texts, int max_tokens, int32_t* h_tokens,
                  int32_t* h_lengths, int32_t* out_max_len);
 
+/* The same rules on the GPU (one CTA per description): the serving path ships the raw bytes of a batch and the token ids
+ * never exist on the host.  t2p_vocab_to_device uploads the hash table once (current device; not during stream capture).
+ * t2p_stage_texts lays the batch out in a HOST (pinned) staging buffer as
+ *   [int32 byte offsets [n_texts + 1] | padding to 16 bytes | the NUL-terminated strings back to back]
+ * (*used_bytes = how much of it the device needs; *all_ascii = 0 if any byte >= 0x80: such batches must take the
+ * Unicode-aware host tokeniser) and, when d_stage != NULL and the batch is ASCII, enqueues that one H2D copy on `stream`.  t2p_tokenize_device reads the device copy of that buffer and writes d_tokens
+ * [n_texts, max_tokens] (zero padded) and d_lengths [n_texts]; a description with more than max_tokens tokens gets length
+ * max_tokens + 1, one longer than 8192 bytes gets -1 (the host checks the lengths it copies back). */
+int t2p_vocab_to_device(t2p_vocab* v);
+size_t t2p_stage_texts_capacity(int n_texts, size_t text_bytes);
+int t2p_stage_texts(const char* texts, size_t total_bytes, int n_texts, void* h_stage, size_t stage_capacity, void* d_stage,
+                    t2p_stream stream, size_t* used_bytes, int* all_ascii);
+int t2p_tokenize_device(const t2p_vocab* v, const void* d_stage, int n_texts, int max_tokens, int32_t* d_tokens,
+                        int32_t* d_lengths, t2p_stream stream);
+
 size_t t2p_lstm_encode_workspace(int B, int H);
 /* d_tokens [B,T] int32 (row b valid for t < d_lengths[b]), 1 <= lengths <= T.  d_out [B,H] =
  * 0.5*(h_fwd_final + h_bwd_final), L2-normalised per row if normalize != 0. */

@@ -81,3 +81,44 @@ def test_engine_pipelined_submit_collect_equals_query(coarse_model):
         eng.collect()
     i0, _ = eng.query(batches[0])  # the synchronous call still works on a pipelined engine
     np.testing.assert_array_equal(i0, want[0][0])
+
+
+def test_device_tokenizer_matches_the_python_rules():
+    """t2p_tokenize_device == models/modules.py:60-72 (remove '.' ',', lower, split on whitespace, OOV -> 0, zero pad) on
+    templated hints and on edge cases: punctuation inside words, runs of separators, empty and over-long descriptions."""
+    from text2pos_cvpr2022_b200 import _lib
+    from text2pos_cvpr2022_b200.modules import tokenize
+
+    kw = {w: i + 1 for i, w in enumerate(syn.known_words())}
+    kw["<unk>"] = 0
+    vocab = _lib.Vocab(kw)
+    vocab.to_device("cuda:0")
+    T = 70
+    texts = syn.synth_queries(3, 40) + [
+        "Hello, World.  The POSE\tis north,of a gray building .", "x", "a.b,c d", " lead and trail \n", "north\x1csouth\x0bwest",
+        "building" * 30 + " north", "The pose is north of a gray-building.", "north " * 70,
+    ]
+    empty_rows = [len(texts), len(texts) + 1]
+    texts += ["", ".,.,  ,"]
+    long_row = len(texts)
+    texts += ["north " * 80]  # 80 tokens > T
+    n = len(texts)
+    cap = _lib.load().t2p_stage_texts_capacity(n, sum(len(t) + 1 for t in texts))
+    h_stage = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    d_stage = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    used, ascii_ = vocab.stage_texts(texts, h_stage, d_stage)
+    assert ascii_ and used <= cap
+    tok = torch.full((n, T), -7, dtype=torch.int32, device="cuda")
+    ln = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    vocab.tokenize_device(d_stage, n, tok, ln)
+    torch.cuda.synchronize()
+    rt, rl = tokenize(texts[:long_row], kw)
+    got_l = ln.cpu().numpy()
+    np.testing.assert_array_equal(got_l[:long_row], rl)
+    assert got_l[long_row] == T + 1 and all(got_l[r] == 0 for r in empty_rows)
+    got = tok.cpu().numpy()
+    np.testing.assert_array_equal(got[:long_row, : rt.shape[1]], rt)
+    assert (got[:long_row, rt.shape[1]:] == 0).all()
+    # non-ASCII batches are flagged for the host tokeniser and not copied
+    _, ascii2 = vocab.stage_texts(["süd of a wall"], h_stage, d_stage)
+    assert not ascii2

@@ -185,3 +185,27 @@ def test_lstm_tensor_core_images_layout_and_split():
     hi_sorted = np.sort(img[:, :, 0].astype(np.float64).reshape(2, -1), axis=1)
     want = np.sort((whh_t * 256.0).astype(np.float16).astype(np.float64).reshape(2, -1), axis=1)
     assert np.array_equal(hi_sorted, want)
+
+
+def test_stage_texts_layout():
+    """t2p_stage_texts (host half of the device tokeniser): [int32 offsets[n+1] | pad to 16 | NUL-terminated strings]."""
+    import torch
+
+    from text2pos_cvpr2022_b200 import _lib
+
+    vocab = _lib.Vocab({"a": 1})
+    texts = ["The pose is north of a gray building.", "", "x y"]
+    lib = _lib.load()
+    cap = lib.t2p_stage_texts_capacity(len(texts), sum(len(t) + 1 for t in texts))
+    assert cap % 16 == 0
+    buf = torch.zeros(cap, dtype=torch.uint8)
+    used, ascii_ = vocab.stage_texts(texts, buf)
+    assert ascii_ and used == cap
+    off = buf[:16].view(torch.int32).tolist()
+    assert off == [0, 38, 39, 43]
+    raw = bytes(buf[16: 16 + 43].tolist())
+    assert raw == b"The pose is north of a gray building.\0\0x y\0"
+    _, ascii2 = vocab.stage_texts(["grün"], buf)
+    assert not ascii2
+    with pytest.raises(RuntimeError):
+        vocab.stage_texts(["x" * 100], torch.zeros(32, dtype=torch.uint8))

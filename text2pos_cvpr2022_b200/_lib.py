@@ -119,6 +119,10 @@ PROTOTYPES = {
     "t2p_vocab_create": (_I, [C.POINTER(C.c_char_p), C.POINTER(C.c_int32), _I, C.POINTER(_P)]),
     "t2p_vocab_destroy": (_I, [_P]),
     "t2p_tokenize": (_I, [_P, C.c_char_p, _SZ, _I, _I, _P, _P, C.POINTER(C.c_int32)]),
+    "t2p_vocab_to_device": (_I, [_P]),
+    "t2p_stage_texts_capacity": (_SZ, [_I, _SZ]),
+    "t2p_stage_texts": (_I, [C.c_char_p, _SZ, _I, _P, _SZ, _P, _P, C.POINTER(_SZ), C.POINTER(_I)]),
+    "t2p_tokenize_device": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "t2p_lstm_encode_workspace": (_SZ, [_I, _I]),
     "t2p_lstm_encode": (_I, [_P, C.POINTER(LstmDesc), _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "t2p_superglue_workspace": (_SZ, [_I, _I, _I, _I]),
@@ -234,6 +238,26 @@ class Vocab:
         check(lib.t2p_tokenize(self.handle, blob, len(blob), n, h_tokens.shape[1], h_tokens.data_ptr(), h_lengths.data_ptr(),
                                C.byref(longest)), "tokenize")
         return int(longest.value)
+
+    def to_device(self, device) -> None:
+        """Upload the hash table for the device tokeniser (once; not during stream capture)."""
+        with torch.cuda.device(device):
+            check(load().t2p_vocab_to_device(self.handle), "vocab_to_device")
+
+    def stage_texts(self, descriptions, h_stage: torch.Tensor, d_stage: torch.Tensor = None):
+        """Lay ``descriptions`` out in the pinned uint8 staging tensor for ``tokenize_device`` and (ASCII batches, if
+        ``d_stage`` is given) enqueue its H2D copy on the current stream; returns (bytes the device needs, all_ascii)."""
+        blob = ("\0".join(descriptions) + "\0").encode("utf-8")
+        used, ascii_ = _SZ(0), _I(0)
+        check(load().t2p_stage_texts(blob, len(blob), len(descriptions), h_stage.data_ptr(), h_stage.numel(),
+                                     None if d_stage is None else d_stage.data_ptr(),
+                                     None if d_stage is None else stream_ptr(d_stage.device), C.byref(used), C.byref(ascii_)),
+              "stage_texts")
+        return int(used.value), bool(ascii_.value)
+
+    def tokenize_device(self, d_stage: torch.Tensor, n_texts: int, d_tokens: torch.Tensor, d_lengths: torch.Tensor) -> None:
+        check(load().t2p_tokenize_device(self.handle, d_stage.data_ptr(), n_texts, d_tokens.shape[1], d_tokens.data_ptr(),
+                                         d_lengths.data_ptr(), stream_ptr(d_tokens.device)), "tokenize_device")
 
     def __del__(self):
         try:

@@ -189,7 +189,8 @@ typedef struct {
   int32_t hidden;      /* H */
   int32_t path;        /* 0 = auto (tensor-core kernel when H == 256, else register kernel, else cluster kernel);
                           1 = shared-memory cluster kernel, 2 = register-resident kernel, 3 = tensor-core kernel */
-  int32_t reserved;
+  int32_t max_groups;  /* tensor-core kernel: clusters per direction a batch is spread over, 1..7; 0 = 7 (lowest latency).
+                          A pipelined server uses 4: ~10% more latency per batch, ~40% less SM-time */
 } t2p_lstm_desc;
 
 /* Host-side tokeniser with the reference's rules (models/modules.py:60-72): '.' and ',' removed, lower-cased, split on

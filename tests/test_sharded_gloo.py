@@ -55,6 +55,11 @@ def _worker(rank, world, port, n, q_out):
         idx, sc = sdb.topk(q, 10)
         ref_i, ref_s = oracle.retrieval.topk(db.numpy(), q.numpy(), 10)
         ok = np.array_equal(idx.numpy(), ref_i) and np.allclose(sc.numpy(), ref_s, rtol=1e-13, atol=0)
+        # data-parallel queries: every rank brings its own batch and gets the global top-k of its own rows
+        q_mine = syn.synth_query_embeddings(10 + rank, 4, 64)
+        idx2, sc2 = sdb.topk_dp(q_mine, 10)
+        ref_i2, ref_s2 = oracle.retrieval.topk(db.numpy(), q_mine.numpy(), 10)
+        ok = ok and np.array_equal(idx2.numpy(), ref_i2) and np.allclose(sc2.numpy(), ref_s2, rtol=1e-13, atol=0)
         q_out.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

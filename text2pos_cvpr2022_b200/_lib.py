@@ -64,7 +64,7 @@ class CellAggDesc(C.Structure):
 class LstmDesc(C.Structure):
     _fields_ = [("xproj_off", C.c_int64), ("whh_off", C.c_int64), ("whh_reg_off", C.c_int64), ("xproj4_off", C.c_int64),
                 ("whh_tc_off", C.c_int64), ("vocab", C.c_int32), ("hidden", C.c_int32), ("path", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("max_groups", C.c_int32)]
 
 
 class SuperGlueDesc(C.Structure):

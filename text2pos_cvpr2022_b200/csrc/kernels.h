@@ -52,6 +52,6 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
 
 // tensor-core LSTM recurrence (H = 256), csrc/lstm_tc.cu
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,
-                   float* hfinal, cudaStream_t s);
+                   float* hfinal, int max_groups, cudaStream_t s);
 
 }  // namespace t2p

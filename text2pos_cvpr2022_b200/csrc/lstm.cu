@@ -561,7 +561,7 @@ int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32
     Arena a(d_ws, ws_bytes);
     float* hfinal = a.take<float>((size_t)2 * B * H);
     T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "lstm_encode: workspace %zu < %zu bytes", ws_bytes, a.used);
-    T2P_TRY(launch_lstm_tc(wptr(w, desc->xproj4_off), wptr(w, desc->whh_tc_off), d_tokens, d_lengths, B, T, V, hfinal, s));
+    T2P_TRY(launch_lstm_tc(wptr(w, desc->xproj4_off), wptr(w, desc->whh_tc_off), d_tokens, d_lengths, B, T, V, hfinal, desc->max_groups, s));
     lstm_finalize_kernel<<<(B + 7) / 8, 256, 0, s>>>(hfinal, B, H, normalize, d_out);
     T2P_LAUNCH_CHECK();
     return T2P_OK;

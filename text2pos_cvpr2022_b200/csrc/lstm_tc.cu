@@ -21,7 +21,6 @@
 // rounding of lo bound the relative error of a product by ~3*2^-22: fp32-grade results (tests: 1e-4 vs the oracle).
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
-#include <cstdlib>
 
 #include "kernels.h"
 #include "sm100.cuh"
@@ -350,16 +349,17 @@ size_t lstm_tc_smem_bytes(int T) {
 }
 
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,
-                   float* hfinal, cudaStream_t s) {
+                   float* hfinal, int max_groups, cudaStream_t s) {
   const size_t smem = lstm_tc_smem_bytes(T);
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "lstm_encode: T=%d needs %zu bytes of shared memory", T, smem);
   T2P_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // The step is bound by the SM-to-SM network (every CTA sends and receives 7/8 KB per sequence of its group), so the
   // batch is spread over as many clusters as B200 co-schedules: at most 15 clusters of 8 CTAs are resident
   // (launch__cluster_max_active), i.e. 7 groups x 2 directions; larger batches run 16 sequences per cluster in waves.
+  // max_groups < 7 trades ~10% latency for SM-time: a pipelined server packs more batches onto the chip with 4 groups.
   int groups, ns;
   if (B <= 7 * LTC_NS) {
-    const int gmax = getenv("T2P_LSTM_GROUPS") ? atoi(getenv("T2P_LSTM_GROUPS")) : 7;
+    const int gmax = (max_groups >= 1 && max_groups <= 7) ? max_groups : 7;
     groups = B < gmax ? B : gmax;
     ns = (B + groups - 1) / groups;
     groups = (B + ns - 1) / ns;

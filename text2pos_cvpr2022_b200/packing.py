@@ -152,6 +152,7 @@ def pack_lstm(bb: BlobBuilder, sd, prefix: str) -> _lib.LstmDesc:
         d.xproj4_off = d.whh_tc_off = -1
     d.vocab, d.hidden = V, H
     d.path = 0
+    d.max_groups = 0
     return d
 
 

@@ -3,7 +3,8 @@
 ``CellDatabase`` keeps the ``[N, D]`` float32 cell embeddings (and the cell-id strings) resident in HBM;
 ``topk`` runs ``t2p_retrieve_topk``.  ``ShardedCellDatabase`` partitions the rows over the ranks of a
 ``torch.distributed`` group (rank r owns rows ``[r*ceil(N/R), ...)``), runs the local top-k, exchanges the
-per-shard lists with ONE all-gather (NCCL over NVLink on GPUs) and merges them with ``t2p_topk_merge``.
+per-shard lists with ONE all-gather (NCCL over NVLink on GPUs) and merges them with ``t2p_topk_merge``
+(``topk``: queries replicated; ``topk_dp``: every rank brings its own query batch, one more all-gather).
 Ordering everywhere: (float64 score descending, index ascending).
 """
 from typing import Callable, List, Optional, Sequence, Tuple
@@ -151,6 +152,32 @@ class ShardedCellDatabase:
         gathered = flat.view(self.world, 2, B, k)
         gs = gathered[:, 0].contiguous().view(torch.float64)  # [R,B,k]
         gi = gathered[:, 1].contiguous()
+        if self._merge is not None:
+            return self._merge(gs, gi, k)
+        return topk_merge(gs, gi, k)
+
+    def topk_dp(self, local_queries: torch.Tensor, k: int):
+        """Data-parallel queries over the sharded DB: every rank passes ITS OWN [B,D] batch (same B on every rank) and
+        gets the global top-k of its own queries.  all-gather of the query embeddings (B*D*4 bytes per rank) -> local
+        top-k of all R*B queries against the shard -> all-gather of the per-shard lists -> merge of the own rows."""
+        B, D = local_queries.shape
+        R, dev = self.world, local_queries.device
+        q_all = torch.empty((R * B, D), dtype=local_queries.dtype, device=dev)
+        self.dist.all_gather_into_tensor(q_all, local_queries.contiguous(), group=self.group)
+        if self.hi > self.lo:
+            if self._local_topk is not None:
+                li, ls = self._local_topk(q_all, self.local, k, self.lo)
+            else:
+                li, ls = retrieve_topk(q_all, self.local, k, self.lo, self._ws, self._norm2_max)
+        else:  # empty shard
+            li = torch.full((R * B, k), -1, dtype=torch.int64, device=dev)
+            ls = torch.full((R * B, k), float("-inf"), dtype=torch.float64, device=dev)
+        packed = torch.stack([ls.view(torch.int64), li], dim=0).contiguous()  # [2, R*B, k]
+        flat = torch.empty((R * 2, R * B, k), dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(flat, packed, group=self.group)
+        mine = flat.view(R, 2, R, B, k)[:, :, self.rank]  # [shard, {score,idx}, B, k]: the rows of this rank's queries
+        gs = mine[:, 0].contiguous().view(torch.float64)
+        gi = mine[:, 1].contiguous()
         if self._merge is not None:
             return self._merge(gs, gi, k)
         return topk_merge(gs, gi, k)

@@ -73,6 +73,11 @@ class OnlineRetrievalEngine:
         self.vocab.to_device(self.device)
         self.max_text_bytes = int(max_text_bytes)  # average bytes per description the staging buffer is sized for
         self.depth = max(1, int(depth))
+        if self.depth > 1:  # throughput mode: fewer, fuller LSTM clusters per batch so that more batches share the chip
+            import copy
+
+            self.lstm_desc = copy.copy(self.lstm_desc)
+            self.lstm_desc.max_groups = 4
         # slot 0 runs on the caller's current stream (query / enqueue_*); further slots own a stream each
         self.slots = [_Slot(self, own_stream=(i > 0 or self.depth > 1)) for i in range(self.depth)]
         self._inflight = collections.deque()
@@ -263,46 +268,125 @@ class OnlineRetrievalEngine:
         return self.h_out.numel() * 8
 
 
+class _ShardSlot:
+    def __init__(self, sh: "ShardedOnlineRetrievalEngine"):
+        e, R = sh.eng, sh.world
+        B, k, D, dev = e.B, e.k, e.D, e.device
+        self.q_all = torch.empty(R * B, D, dtype=torch.float32, device=dev)
+        self.loc = torch.empty(2, R * B, k, dtype=torch.int64, device=dev)          # [score bits | global idx] of all R*B queries
+        self.gathered = torch.empty(R * 2, R * B, k, dtype=torch.int64, device=dev)  # every shard's lists
+        self.mine = torch.empty(2, R, B, k, dtype=torch.int64, device=dev)           # this rank's queries: [score|idx][shard]
+        n_len64 = (B + 1) // 2
+        self.d_final = torch.zeros(2 * B * k + n_len64, dtype=torch.int64, device=dev)
+        self.h_final = torch.zeros(2 * B * k + n_len64, dtype=torch.int64).pin_memory()
+        self.final_scores = self.d_final[: B * k].view(torch.float64).view(B, k)
+        self.final_idx = self.d_final[B * k: 2 * B * k].view(B, k)
+        self.final_counts = self.d_final[2 * B * k:].view(torch.int32)[:B]
+        self.h_scores = self.h_final[: B * k].view(torch.float64).view(B, k)
+        self.h_idx = self.h_final[B * k: 2 * B * k].view(B, k)
+        self.h_counts = self.h_final[2 * B * k:].view(torch.int32)[:B].numpy()
+        with torch.cuda.device(dev):
+            n = e.lib.t2p_retrieve_topk_workspace(R * B, e.db.shape[0], e.db.shape[1], k)
+            self.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=dev)
+            self.done = torch.cuda.Event()
+
+
 class ShardedOnlineRetrievalEngine:
-    """One ``OnlineRetrievalEngine`` per rank over its row shard of the DB (``idx_base`` = first row); queries are
-    replicated.  ``step``/``query`` = local step -> ONE all-gather of the packed [2, B, k] int64 result (score bits,
-    global index; 10 KB per rank at B=64, k=10) -> ``t2p_topk_merge`` on every rank."""
+    """Data-parallel queries over a row-sharded DB: one ``OnlineRetrievalEngine`` per rank over its shard (``idx_base`` =
+    first row).  Every rank brings ITS OWN batch of B queries per step (global batch R*B):
+
+        device tokeniser + text encoder (own B queries)
+        -> all-gather of the query embeddings            (B*D*4 = 64 KB per rank)
+        -> local top-k of all R*B queries against the shard
+        -> all-gather of the per-shard top-k lists       (R*B*k*16 bytes per rank)
+        -> ``t2p_topk_merge`` of the R lists of the own B queries.
+
+    No rank repeats another rank's text encoding; the exchange volume is independent of the DB size.  ``submit`` /
+    ``collect`` pipeline ``engine.depth`` batches like the single-GPU engine (collectives are issued in the same slot
+    order on every rank)."""
 
     def __init__(self, engine: OnlineRetrievalEngine, group=None):
         import torch.distributed as dist
 
         self.dist, self.group, self.eng = dist, group, engine
         self.world = dist.get_world_size(group)
-        B, k, dev = engine.B, engine.k, engine.device
-        self.gathered = torch.empty((self.world, 2, B, k), dtype=torch.int64, device=dev)
-        self.d_final = torch.empty(2 * B * k, dtype=torch.int64, device=dev)
-        self.h_final = torch.empty(2 * B * k, dtype=torch.int64).pin_memory()
-        self.final_scores = self.d_final[: B * k].view(torch.float64).view(B, k)
-        self.final_idx = self.d_final[B * k:].view(B, k)
+        self.rank = dist.get_rank(group)
+        self.slots = [_ShardSlot(self) for _ in range(engine.depth)]
+        self._inflight = collections.deque()
+        self._next = 0
 
-    def enqueue_exchange(self):
-        """all-gather + merge of the local result that ``engine.enqueue_step`` left in ``engine.d_out``."""
-        e = self.eng
-        self.dist.all_gather_into_tensor(self.gathered.view(self.world * 2, e.B, e.k), e.d_out[: 2 * e.B * e.k].view(2, e.B, e.k), group=self.group)
-        # gathered[r, 0] / [r, 1] are contiguous [B, k] blocks: the merge kernel takes the two [R, B, k] arrays as strided
-        # views only if contiguous, so split once (2 x R*B*k*8 bytes, device-to-device)
-        gs = self.gathered[:, 0].contiguous().view(torch.float64)
-        gi = self.gathered[:, 1].contiguous()
+    def enqueue_exchange(self, db: Optional[torch.Tensor] = None, slot: int = 0):
+        """Everything after the text encoder of ``engine.slots[slot]``: gather queries, local top-k, gather lists, merge."""
+        e, s, R = self.eng, self.slots[slot], self.world
+        es = e.slots[slot]
+        B, k = e.B, e.k
+        db = e.db if db is None else db
+        self.dist.all_gather_into_tensor(s.q_all, es.q, group=self.group)
         _lib.check(
-            e.lib.t2p_topk_merge(gs.data_ptr(), gi.data_ptr(), self.world, e.B, e.k, e.k, self.final_scores.data_ptr(),
-                                 self.final_idx.data_ptr(), _lib.stream_ptr(e.device)),
+            e.lib.t2p_retrieve_topk_ex(s.q_all.data_ptr(), db.data_ptr(), R * B, db.shape[0], db.shape[1], k, e.idx_base,
+                                       e.db_norm2_max.data_ptr(), 0, s.loc[0].data_ptr(), s.loc[1].data_ptr(),
+                                       e.stats.data_ptr(), s.ws_topk.data_ptr(), s.ws_topk.numel(), _lib.stream_ptr(e.device)),
+            "retrieve_topk",
+        )
+        self.dist.all_gather_into_tensor(s.gathered, s.loc, group=self.group)
+        # rows of this rank's queries from every shard: [shard, {score,idx}, B, k] -> [{score,idx}, shard, B, k]
+        s.mine.copy_(s.gathered.view(R, 2, R, B, k)[:, :, self.rank].permute(1, 0, 2, 3))
+        _lib.check(
+            e.lib.t2p_topk_merge(s.mine[0].data_ptr(), s.mine[1].data_ptr(), R, B, k, k, s.final_scores.data_ptr(),
+                                 s.final_idx.data_ptr(), _lib.stream_ptr(e.device)),
             "topk_merge",
         )
 
-    def query(self, descriptions: List[str], graph_key=None):
+    def enqueue_step(self, db: Optional[torch.Tensor] = None, slot: int = 0, tokenize: bool = True):
         e = self.eng
-        on_device = e._stage(descriptions, 0)
-        if on_device and graph_key is not None and graph_key in e._graphs:
-            e._graphs[graph_key].replay()
+        if tokenize:
+            e.enqueue_tokenize(slot)
+        e.enqueue_encode(slot=slot)
+        self.enqueue_exchange(db, slot)
+
+    def _enqueue_query(self, slot: int, descriptions):
+        e, s = self.eng, self.slots[slot]
+        on_device = e._stage(descriptions, slot)
+        self.enqueue_step(slot=slot, tokenize=on_device)
+        s.final_counts.copy_(e.slots[slot].lengths)
+        s.h_final.copy_(s.d_final, non_blocking=True)
+
+    def _check(self, s: _ShardSlot):
+        self.eng._check_counts(s)  # same checks as the local engine, on this slot's token counts
+
+    def query(self, descriptions: List[str], graph_key=None):
+        """This rank's B strings -> (idx [B,k] global int64, scores [B,k] float64) numpy; collective: every rank calls it."""
+        if self._inflight:
+            raise RuntimeError("query() while submitted batches are in flight: collect() them first")
+        e, s = self.eng, self.slots[0]
+        st = e.slots[0].stream
+        if st is not None:
+            with torch.cuda.stream(st):
+                self._enqueue_query(0, descriptions)
+            st.synchronize()
         else:
-            e.enqueue_step(tokenize=on_device)
-        self.enqueue_exchange()
-        self.h_final.copy_(self.d_final, non_blocking=True)
-        torch.cuda.current_stream(e.device).synchronize()
-        B, k = e.B, e.k
-        return self.h_final[B * k:].view(B, k).numpy(), self.h_final[: B * k].view(torch.float64).view(B, k).numpy()
+            self._enqueue_query(0, descriptions)
+            torch.cuda.current_stream(e.device).synchronize()
+        self._check(s)
+        return s.h_idx.numpy(), s.h_scores.numpy()
+
+    def submit(self, descriptions: List[str], graph_key=None) -> int:
+        e = self.eng
+        if e.depth < 2:
+            raise RuntimeError("submit() needs an engine built with depth >= 2")
+        if len(self._inflight) >= e.depth:
+            raise RuntimeError(f"{e.depth} batches already in flight: collect() first")
+        slot = self._next
+        with torch.cuda.stream(e.slots[slot].stream):
+            self._enqueue_query(slot, descriptions)
+            self.slots[slot].done.record()
+        self._next = (self._next + 1) % e.depth
+        self._inflight.append(slot)
+        return slot
+
+    def collect(self):
+        slot = self._inflight.popleft()
+        s = self.slots[slot]
+        s.done.synchronize()
+        self._check(s)
+        return s.h_idx.numpy(), s.h_scores.numpy()

@@ -218,7 +218,7 @@ def main_b200(args):
 
     depth = max(1, args.depth)  # batches in flight (one stream per slot)
     eng = OnlineRetrievalEngine(model, base, k=TOPK, max_batch=B_QUERIES, max_tokens=T, idx_base=lo, depth=depth)
-    sharded = ShardedOnlineRetrievalEngine(eng) if world > 1 else None
+    sharded = ShardedOnlineRetrievalEngine(eng, exchange=args.exchange) if world > 1 else None
     user = sharded if sharded is not None else eng
     q_per_step = B_QUERIES * world  # whole job
 
@@ -308,9 +308,9 @@ def main_b200(args):
     # ---- e2e: host strings in, host indices out, through the public engine call --------------------------------------
     # every step: raw text into pinned memory + ONE H2D copy (one native call), the step (N = 1: a captured CUDA graph per
     # rotating DB copy), ONE D2H copy, event synchronise at collect(); `depth` batches in flight
-    if world == 1:
+    if world == 1 or args.exchange == "p2p":
         for key in range(N_DB_COPIES):
-            eng.capture_all(key, copies[key])
+            user.capture_all(key, copies[key])
     n_e2e = max(20, min(K, 500))
 
     def e2e_loop(n):
@@ -343,7 +343,8 @@ def main_b200(args):
            "d2h_bytes_per_step": eng.d2h_bytes() * world, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
            "call": call + " -> (idx, scores) numpy per rank: raw text staged into pinned memory, 1 H2D copy, " +
                    ("CUDA graph of the 5 kernels (device tokeniser first)" if world == 1 else
-                    "5 kernels + 2 all-gathers + merge") + ", 1 D2H copy, synchronise"}
+                    ("CUDA graph of 5 kernels + 2 peer pushes/waits over NVLink IPC memory + merge" if args.exchange == "p2p" else
+                     "5 kernels + 2 NCCL all-gathers + merge")) + ", 1 D2H copy, synchronise"}
 
     # ---- parity guard against the oracle over the FULL DB (every rank checks its own queries) ---------------------------
     import oracle
@@ -385,7 +386,8 @@ def main_b200(args):
         cpu = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     par = "single GPU" if world == 1 else (f"queries data-parallel ({B_QUERIES}/GPU), DB row-sharded x{world}; all-gather of query "
-                                           "embeddings + all-gather of per-shard top-k")
+                                           "embeddings + exchange of per-shard top-k, " +
+                                           ("own push/wait kernels over CUDA-IPC peer memory (NVLink)" if args.exchange == "p2p" else "NCCL"))
     line = {
         "metric": "queries/sec coarse top-10 retrieval", "value": q_per_step * K / (total_ms * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -395,7 +397,7 @@ def main_b200(args):
                    "cells_per_gpu": n_local, "l2": f"{N_DB_COPIES} rotating DB copies ({N_DB_COPIES * n_local * EMBED * 4 / 1e6:.0f} MB > L2)",
                    "weights": "random-init", "parallelism": par},
         "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": (OnlineRetrievalEngine.KERNELS_PER_STEP + (1 if world > 1 else 0)) * K * world,
+        "gpu_launches": (OnlineRetrievalEngine.KERNELS_PER_STEP + ((5 if args.exchange == "p2p" else 1) if world > 1 else 0)) * K * world,
         "pipeline": {"depth": depth, "serial_ms_per_step": serial_ms_step, "serial_value": q_per_step / (serial_ms_step * 1e-3),
                      "note": "value/ms_per_step: `depth` batches in flight on separate streams; roofline kernel times: serial pass"},
         "tensor_path_queries": {"certified": stats[0], "rescanned_exactly": stats[1]},
@@ -413,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange: own peer-memory kernels or NCCL")
     ap.add_argument("--depth", type=int, default=4, help="batches in flight (one stream per slot)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -90,6 +90,27 @@ int t2p_topk_merge(const double* d_scores, const int64_t* d_idx, int R, int B, i
                    double* d_out_scores, int64_t* d_out_idx, t2p_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Peer exchange of the sharded retrieval over NVLink peer memory, no NCCL on the data path.  Every rank
+ * owns one buffer that its peers have mapped (CUDA IPC); `base[j]` is rank j's buffer as seen from THIS process.
+ * t2p_peer_push: for every peer j, copies bytes0 from d_src0 + j*src_stride0 to base[j] + dst_off0 (and optionally a
+ *   second block), then raises the 64-bit flag at base[j] + flag_off to (*d_epoch + 1).
+ * t2p_peer_wait: spins (on the device) until the n_peers local flags at d_flags are all > *d_epoch, then increments
+ *   *d_epoch.  Epochs live on the device and advance in step on every rank, so push/wait pairs can be captured in CUDA
+ *   graphs.  A peer that never arrives traps after ~30 s (CUDA error at the caller) instead of hanging.
+ * ------------------------------------------------------------------------------------------------ */
+#define T2P_MAX_PEERS 8
+typedef struct {
+  void* base[T2P_MAX_PEERS];
+  int32_t n_peers;
+  int32_t my_rank;
+} t2p_peers;
+int t2p_enable_peer_access(int peer_device);
+int t2p_peer_push(const t2p_peers* peers, const void* d_src0, size_t src_stride0, size_t dst_off0, size_t bytes0,
+                  const void* d_src1, size_t src_stride1, size_t dst_off1, size_t bytes1, size_t flag_off,
+                  const uint64_t* d_epoch, t2p_stream stream);
+int t2p_peer_wait(uint64_t* d_flags, int n_peers, uint64_t* d_epoch, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (a2) PointNet++ primitives, exposed for bit-exact index parity.
  * Replaces torch_geometric fps()/radius() at models/pointcloud/pointnet2.py:26,28-30.
  * d_pos [n_obj,P,3].  fps: start index 0, ties -> lowest index, m samples in selection order.

@@ -67,6 +67,13 @@ class LstmDesc(C.Structure):
                 ("max_groups", C.c_int32)]
 
 
+MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    _fields_ = [("base", C.c_void_p * MAX_PEERS), ("n_peers", C.c_int32), ("my_rank", C.c_int32)]
+
+
 class SuperGlueDesc(C.Structure):
     _fields_ = [
         ("q", LinearDesc * MAX_GNN_LAYERS),
@@ -102,6 +109,9 @@ PROTOTYPES = {
     "t2p_retrieve_topk_ex": (_I, [_P, _P, _I, _I, _I, _I, C.c_int64, _P, _I, _P, _P, _P, _P, _SZ, _P]),
     "t2p_db_row_norm2_max": (_I, [_P, _I, _I, _P, _P]),
     "t2p_topk_merge": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "t2p_enable_peer_access": (_I, [_I]),
+    "t2p_peer_push": (_I, [C.POINTER(Peers), _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, _SZ, _P, _P]),
+    "t2p_peer_wait": (_I, [_P, _I, _P, _P]),
     "t2p_fps": (_I, [_P, _I, _I, _I, _P, _P]),
     "t2p_ball_query": (_I, [_P, _P, _I, _I, _I, C.c_float, _I, _P, _P, _P]),
     "t2p_linear": (_I, [_P, C.POINTER(LinearDesc), _P, _I, _I, _I, _P, _I, _P]),

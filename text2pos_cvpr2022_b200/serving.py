@@ -272,10 +272,20 @@ class _ShardSlot:
     def __init__(self, sh: "ShardedOnlineRetrievalEngine"):
         e, R = sh.eng, sh.world
         B, k, D, dev = e.B, e.k, e.D, e.device
-        self.q_all = torch.empty(R * B, D, dtype=torch.float32, device=dev)
+        # symmetric region (mapped by the peers in p2p mode): [q_all R*B*D f32 | mine 2*R*B*k i64 | flags 2*R u64]
+        al = lambda x: (x + 255) // 256 * 256
+        self.q_all_off, q_bytes = 0, R * B * D * 4
+        self.mine_off, m_bytes = al(q_bytes), 2 * R * B * k * 8
+        self.flags_off = al(self.mine_off + m_bytes)
+        self.sym = torch.zeros(self.flags_off + al(2 * R * 8), dtype=torch.uint8, device=dev)
+        self.q_all = self.sym[: q_bytes].view(torch.float32).view(R * B, D)
+        self.mine = self.sym[self.mine_off: self.mine_off + m_bytes].view(torch.int64).view(2, R, B, k)  # own queries: [score|idx][shard]
+        self.flags = self.sym[self.flags_off: self.flags_off + 2 * R * 8].view(torch.int64)                # [exchange][source rank]
+        self.epochs = torch.zeros(2, dtype=torch.int64, device=dev)                                         # local, one per exchange
+        self.peers = None          # _lib.Peers of this slot's region on every rank (p2p mode)
+        self.peer_tensors = None   # keeps the IPC mappings alive
         self.loc = torch.empty(2, R * B, k, dtype=torch.int64, device=dev)          # [score bits | global idx] of all R*B queries
-        self.gathered = torch.empty(R * 2, R * B, k, dtype=torch.int64, device=dev)  # every shard's lists
-        self.mine = torch.empty(2, R, B, k, dtype=torch.int64, device=dev)           # this rank's queries: [score|idx][shard]
+        self.gathered = None                                                         # every shard's lists (NCCL mode only)
         n_len64 = (B + 1) // 2
         self.d_final = torch.zeros(2 * B * k + n_len64, dtype=torch.int64, device=dev)
         self.h_final = torch.zeros(2 * B * k + n_len64, dtype=torch.int64).pin_memory()
@@ -289,6 +299,7 @@ class _ShardSlot:
             n = e.lib.t2p_retrieve_topk_workspace(R * B, e.db.shape[0], e.db.shape[1], k)
             self.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=dev)
             self.done = torch.cuda.Event()
+        self.graphs = {}
 
 
 class ShardedOnlineRetrievalEngine:
@@ -305,35 +316,90 @@ class ShardedOnlineRetrievalEngine:
     ``collect`` pipeline ``engine.depth`` batches like the single-GPU engine (collectives are issued in the same slot
     order on every rank)."""
 
-    def __init__(self, engine: OnlineRetrievalEngine, group=None):
+    def __init__(self, engine: OnlineRetrievalEngine, group=None, exchange: str = "p2p"):
+        """``exchange``: "p2p" = own push/wait kernels over CUDA-IPC peer memory (NVLink; CUDA-graph capturable, nothing of
+        NCCL on the data path), "nccl" = two ``all_gather_into_tensor`` calls per step."""
         import torch.distributed as dist
 
         self.dist, self.group, self.eng = dist, group, engine
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange == "p2p" and self.world > _lib.MAX_PEERS:
+            raise ValueError(f"p2p exchange supports up to {_lib.MAX_PEERS} ranks (one NVLink domain)")
+        self.exchange = exchange
         self.slots = [_ShardSlot(self) for _ in range(engine.depth)]
         self._inflight = collections.deque()
         self._next = 0
+        if exchange == "p2p":
+            self._map_peers()
+        else:
+            # one communicator (hence one NCCL stream) per slot: collectives of different slots must not queue behind
+            # each other, or the shared NCCL stream would serialise the batches in flight
+            ranks = dist.get_process_group_ranks(group) if group is not None else list(range(self.world))
+            self.groups = [group] + [dist.new_group(ranks) for _ in range(engine.depth - 1)]
+            R, B, k = self.world, engine.B, engine.k
+            for s in self.slots:
+                s.gathered = torch.empty(R * 2, R * B, k, dtype=torch.int64, device=engine.device)
+
+    def _map_peers(self):
+        """Exchange CUDA-IPC handles of every slot's symmetric region (host side, once) and map the peers' regions."""
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        e = self.eng
+        torch.cuda.synchronize(e.device)
+        mine = [reduce_tensor(s.sym) for s in self.slots]
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine, group=self.group)
+        with torch.cuda.device(e.device):
+            for i, s in enumerate(self.slots):
+                s.peer_tensors = [s.sym if r == self.rank else everyone[r][i][0](*everyone[r][i][1]) for r in range(self.world)]
+                p = _lib.Peers()
+                p.n_peers, p.my_rank = self.world, self.rank
+                for r, t in enumerate(s.peer_tensors):
+                    _lib.check(e.lib.t2p_enable_peer_access(t.device.index), "enable_peer_access")
+                    p.base[r] = t.data_ptr()
+                s.peers = p
+        self.dist.barrier(group=self.group)  # nobody pushes before every rank has mapped every region
+
+    def _topk_all(self, s, db):
+        e, R = self.eng, self.world
+        _lib.check(
+            e.lib.t2p_retrieve_topk_ex(s.q_all.data_ptr(), db.data_ptr(), R * e.B, db.shape[0], db.shape[1], e.k, e.idx_base,
+                                       e.db_norm2_max.data_ptr(), 0, s.loc[0].data_ptr(), s.loc[1].data_ptr(),
+                                       e.stats.data_ptr(), s.ws_topk.data_ptr(), s.ws_topk.numel(), _lib.stream_ptr(e.device)),
+            "retrieve_topk",
+        )
 
     def enqueue_exchange(self, db: Optional[torch.Tensor] = None, slot: int = 0):
         """Everything after the text encoder of ``engine.slots[slot]``: gather queries, local top-k, gather lists, merge."""
         e, s, R = self.eng, self.slots[slot], self.world
         es = e.slots[slot]
-        B, k = e.B, e.k
+        B, k, D = e.B, e.k, e.D
         db = e.db if db is None else db
-        self.dist.all_gather_into_tensor(s.q_all, es.q, group=self.group)
-        _lib.check(
-            e.lib.t2p_retrieve_topk_ex(s.q_all.data_ptr(), db.data_ptr(), R * B, db.shape[0], db.shape[1], k, e.idx_base,
-                                       e.db_norm2_max.data_ptr(), 0, s.loc[0].data_ptr(), s.loc[1].data_ptr(),
-                                       e.stats.data_ptr(), s.ws_topk.data_ptr(), s.ws_topk.numel(), _lib.stream_ptr(e.device)),
-            "retrieve_topk",
-        )
-        self.dist.all_gather_into_tensor(s.gathered, s.loc, group=self.group)
-        # rows of this rank's queries from every shard: [shard, {score,idx}, B, k] -> [{score,idx}, shard, B, k]
-        s.mine.copy_(s.gathered.view(R, 2, R, B, k)[:, :, self.rank].permute(1, 0, 2, 3))
+        st = _lib.stream_ptr(e.device)
+        if self.exchange == "p2p":
+            lib, blk = e.lib, B * k * 8
+            # q [B,D] -> every peer's q_all[rank]; then wait for the R blocks of this rank's q_all
+            _lib.check(lib.t2p_peer_push(s.peers, es.q.data_ptr(), 0, s.q_all_off + self.rank * B * D * 4, B * D * 4,
+                                         None, 0, 0, 0, s.flags_off + (0 * R + self.rank) * 8, s.epochs[0:].data_ptr(), st), "peer_push")
+            _lib.check(lib.t2p_peer_wait(s.flags[0:].data_ptr(), R, s.epochs[0:].data_ptr(), st), "peer_wait")
+            self._topk_all(s, db)
+            # lists of peer j's queries (rows j*B..) -> peer j's mine[score|idx][rank]; then wait for the R lists of the own rows
+            _lib.check(lib.t2p_peer_push(s.peers, s.loc[0].data_ptr(), blk, s.mine_off + (0 * R + self.rank) * blk, blk,
+                                         s.loc[1].data_ptr(), blk, s.mine_off + (1 * R + self.rank) * blk, blk,
+                                         s.flags_off + (1 * R + self.rank) * 8, s.epochs[1:].data_ptr(), st), "peer_push")
+            _lib.check(lib.t2p_peer_wait(s.flags[R:].data_ptr(), R, s.epochs[1:].data_ptr(), st), "peer_wait")
+        else:
+            self.dist.all_gather_into_tensor(s.q_all, es.q, group=self.groups[slot])
+            self._topk_all(s, db)
+            self.dist.all_gather_into_tensor(s.gathered, s.loc, group=self.groups[slot])
+            # rows of this rank's queries from every shard: [shard, {score,idx}, B, k] -> [{score,idx}, shard, B, k]
+            s.mine.copy_(s.gathered.view(R, 2, R, B, k)[:, :, self.rank].permute(1, 0, 2, 3))
         _lib.check(
             e.lib.t2p_topk_merge(s.mine[0].data_ptr(), s.mine[1].data_ptr(), R, B, k, k, s.final_scores.data_ptr(),
-                                 s.final_idx.data_ptr(), _lib.stream_ptr(e.device)),
+                                 s.final_idx.data_ptr(), st),
             "topk_merge",
         )
 
@@ -344,11 +410,38 @@ class ShardedOnlineRetrievalEngine:
         e.enqueue_encode(slot=slot)
         self.enqueue_exchange(db, slot)
 
-    def _enqueue_query(self, slot: int, descriptions):
+    def capture(self, key=0, db: Optional[torch.Tensor] = None, slot: int = 0):
+        """p2p mode: capture one whole sharded step of ``slot`` (tokeniser .. merge, pushes and waits included) into a CUDA
+        graph.  Collective: every rank must capture (it runs one real step first) and later replay in the same order."""
+        if self.exchange != "p2p":
+            raise RuntimeError("only the p2p exchange is captured into CUDA graphs")
+        e = self.eng
+        with torch.cuda.device(e.device):
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                self.enqueue_step(db, slot=slot)
+            torch.cuda.current_stream().wait_stream(st)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue_step(db, slot=slot)
+                self.slots[slot].final_counts.copy_(e.slots[slot].lengths)
+            self.slots[slot].graphs[key] = g
+        return g
+
+    def capture_all(self, key=0, db: Optional[torch.Tensor] = None):
+        for i in range(self.eng.depth):
+            self.capture(key, db, slot=i)
+
+    def _enqueue_query(self, slot: int, descriptions, graph_key=None):
         e, s = self.eng, self.slots[slot]
         on_device = e._stage(descriptions, slot)
-        self.enqueue_step(slot=slot, tokenize=on_device)
-        s.final_counts.copy_(e.slots[slot].lengths)
+        if on_device and graph_key is not None and graph_key in s.graphs:
+            s.graphs[graph_key].replay()
+        else:
+            self.enqueue_step(slot=slot, tokenize=on_device)
+            s.final_counts.copy_(e.slots[slot].lengths)
         s.h_final.copy_(s.d_final, non_blocking=True)
 
     def _check(self, s: _ShardSlot):
@@ -362,10 +455,10 @@ class ShardedOnlineRetrievalEngine:
         st = e.slots[0].stream
         if st is not None:
             with torch.cuda.stream(st):
-                self._enqueue_query(0, descriptions)
+                self._enqueue_query(0, descriptions, graph_key)
             st.synchronize()
         else:
-            self._enqueue_query(0, descriptions)
+            self._enqueue_query(0, descriptions, graph_key)
             torch.cuda.current_stream(e.device).synchronize()
         self._check(s)
         return s.h_idx.numpy(), s.h_scores.numpy()
@@ -378,7 +471,7 @@ class ShardedOnlineRetrievalEngine:
             raise RuntimeError(f"{e.depth} batches already in flight: collect() first")
         slot = self._next
         with torch.cuda.stream(e.slots[slot].stream):
-            self._enqueue_query(slot, descriptions)
+            self._enqueue_query(slot, descriptions, graph_key)
             self.slots[slot].done.record()
         self._next = (self._next + 1) % e.depth
         self._inflight.append(slot)

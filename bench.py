@@ -358,6 +358,8 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         parity_ok = bool(t.item())
 
+    if sharded is not None:
+        sharded.close()
     if rank != 0:
         dist.destroy_process_group()
         return

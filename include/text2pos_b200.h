@@ -105,6 +105,13 @@ typedef struct {
   int32_t my_rank;
 } t2p_peers;
 int t2p_enable_peer_access(int peer_device);
+/* symmetric buffers: a zero-filled cudaMalloc block + its 64-byte CUDA IPC handle (the host side ships the handles to the
+ * peers, e.g. with all_gather_object); t2p_ipc_open maps a peer's block into this process (call it with the CONSUMER's
+ * device current: peer access is enabled lazily).  The owner frees with t2p_ipc_free after the peers have closed. */
+int t2p_ipc_alloc(size_t bytes, void** d_ptr, void* handle64);
+int t2p_ipc_open(const void* handle64, void** d_ptr);
+int t2p_ipc_close(void* d_ptr);
+int t2p_ipc_free(void* d_ptr);
 int t2p_peer_push(const t2p_peers* peers, const void* d_src0, size_t src_stride0, size_t dst_off0, size_t bytes0,
                   const void* d_src1, size_t src_stride1, size_t dst_off1, size_t bytes1, size_t flag_off,
                   const uint64_t* d_epoch, t2p_stream stream);

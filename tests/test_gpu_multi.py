@@ -61,6 +61,7 @@ def _worker(rank, world, port, exchange, q_out):
         while sh._inflight:
             got.append(sh.collect()[0].copy())
         ok = ok and all(np.array_equal(a, b) for a, b in zip(got, want))
+        sh.close()
         q_out.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -79,7 +80,7 @@ def test_sharded_engine_data_parallel(exchange):
     procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, q_out)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q_out.get(timeout=240) for _ in range(world)]
+    res = [q_out.get(timeout=150) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]

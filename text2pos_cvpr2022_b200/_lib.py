@@ -110,6 +110,10 @@ PROTOTYPES = {
     "t2p_db_row_norm2_max": (_I, [_P, _I, _I, _P, _P]),
     "t2p_topk_merge": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "t2p_enable_peer_access": (_I, [_I]),
+    "t2p_ipc_alloc": (_I, [_SZ, C.POINTER(_P), _P]),
+    "t2p_ipc_open": (_I, [_P, C.POINTER(_P)]),
+    "t2p_ipc_close": (_I, [_P]),
+    "t2p_ipc_free": (_I, [_P]),
     "t2p_peer_push": (_I, [C.POINTER(Peers), _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, _SZ, _P, _P]),
     "t2p_peer_wait": (_I, [_P, _I, _P, _P]),
     "t2p_fps": (_I, [_P, _I, _I, _I, _P, _P]),
@@ -187,6 +191,50 @@ def stream_ptr(device=None) -> int:
 def require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"text2pos_b200: {what} must live on a CUDA device (sm_100a); there is no CPU path")
+
+
+class _RawCuda:
+    """``__cuda_array_interface__`` view of raw device memory (for ``torch.as_tensor``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class SymmetricBuffer:
+    """A zero-filled cudaMalloc block of this rank that the peers map over CUDA IPC (``t2p_ipc_*``); ``tensor`` is a
+    uint8 torch view of the local block, ``handle`` the 64 bytes to ship to the peers, ``open_peer`` maps theirs."""
+
+    def __init__(self, nbytes: int, device):
+        self.lib = load()
+        self.device = torch.device(device)
+        self.nbytes = int(nbytes)
+        p, h = _P(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(self.lib.t2p_ipc_alloc(self.nbytes, C.byref(p), h), "ipc_alloc")
+            self.ptr = int(p.value)
+            self.tensor = torch.as_tensor(_RawCuda(self.ptr, self.nbytes), device=self.device)
+        self.handle = bytes(h.raw)
+        self.peer_ptrs = []
+
+    def open_peer(self, handle: bytes) -> int:
+        p = _P()
+        with torch.cuda.device(self.device):
+            check(self.lib.t2p_ipc_open(C.create_string_buffer(handle, 64), C.byref(p)), "ipc_open")
+        self.peer_ptrs.append(int(p.value))
+        return int(p.value)
+
+    def close(self):
+        try:
+            with torch.cuda.device(self.device):
+                for q in self.peer_ptrs:
+                    self.lib.t2p_ipc_close(q)
+                self.peer_ptrs = []
+                if self.ptr:
+                    self.tensor = None
+                    self.lib.t2p_ipc_free(self.ptr)
+                    self.ptr = 0
+        except Exception:
+            pass
 
 
 class Workspace:

@@ -10,6 +10,8 @@
 // sequence, so the device-resident epochs stay in step without any host value -- the whole step is CUDA-graph capturable.
 // Buffer reuse needs no back-pressure: a rank can only push step s+depth of a slot after its own step s of that slot
 // has completed, which required every peer to have consumed step s (see serving.py).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace t2p {
@@ -75,6 +77,45 @@ int t2p_enable_peer_access(int peer_device) {
     return T2P_OK;
   }
   T2P_CUDA(e);
+  return T2P_OK;
+}
+
+// Symmetric buffers are plain cudaMalloc allocations shared through legacy CUDA IPC handles: peer access
+// (cudaDeviceEnablePeerAccess / lazily at open) covers them for KERNEL loads and stores, which is not the case for the
+// VMM-backed blocks of a caching allocator (measured: kernels fault on torch-IPC tensors of another device).
+int t2p_ipc_alloc(size_t bytes, void** d_ptr, void* handle64) {
+  T2P_REQUIRE(d_ptr && handle64 && bytes > 0, T2P_ERR_INVALID, "ipc_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  void* p = nullptr;
+  T2P_CUDA(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    t2p::set_error("ipc_alloc: %s", cudaGetErrorString(e));
+    return T2P_ERR_CUDA;
+  }
+  memcpy(handle64, &h, sizeof(h));
+  *d_ptr = p;
+  return T2P_OK;
+}
+
+int t2p_ipc_open(const void* handle64, void** d_ptr) {
+  T2P_REQUIRE(handle64 && d_ptr, T2P_ERR_INVALID, "ipc_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  T2P_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return T2P_OK;
+}
+
+int t2p_ipc_close(void* d_ptr) {
+  if (d_ptr) T2P_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return T2P_OK;
+}
+
+int t2p_ipc_free(void* d_ptr) {
+  if (d_ptr) T2P_CUDA(cudaFree(d_ptr));
   return T2P_OK;
 }
 

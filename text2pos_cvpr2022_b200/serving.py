@@ -277,13 +277,18 @@ class _ShardSlot:
         self.q_all_off, q_bytes = 0, R * B * D * 4
         self.mine_off, m_bytes = al(q_bytes), 2 * R * B * k * 8
         self.flags_off = al(self.mine_off + m_bytes)
-        self.sym = torch.zeros(self.flags_off + al(2 * R * 8), dtype=torch.uint8, device=dev)
+        sym_bytes = self.flags_off + al(2 * R * 8)
+        if sh.exchange == "p2p":  # a cudaMalloc block with a CUDA IPC handle (kernels of the peers store into it over NVLink)
+            self.sym_buf = _lib.SymmetricBuffer(sym_bytes, dev)
+            self.sym = self.sym_buf.tensor
+        else:
+            self.sym_buf = None
+            self.sym = torch.zeros(sym_bytes, dtype=torch.uint8, device=dev)
         self.q_all = self.sym[: q_bytes].view(torch.float32).view(R * B, D)
         self.mine = self.sym[self.mine_off: self.mine_off + m_bytes].view(torch.int64).view(2, R, B, k)  # own queries: [score|idx][shard]
         self.flags = self.sym[self.flags_off: self.flags_off + 2 * R * 8].view(torch.int64)                # [exchange][source rank]
         self.epochs = torch.zeros(2, dtype=torch.int64, device=dev)                                         # local, one per exchange
         self.peers = None          # _lib.Peers of this slot's region on every rank (p2p mode)
-        self.peer_tensors = None   # keeps the IPC mappings alive
         self.loc = torch.empty(2, R * B, k, dtype=torch.int64, device=dev)          # [score bits | global idx] of all R*B queries
         self.gathered = None                                                         # every shard's lists (NCCL mode only)
         n_len64 = (B + 1) // 2
@@ -344,24 +349,28 @@ class ShardedOnlineRetrievalEngine:
                 s.gathered = torch.empty(R * 2, R * B, k, dtype=torch.int64, device=engine.device)
 
     def _map_peers(self):
-        """Exchange CUDA-IPC handles of every slot's symmetric region (host side, once) and map the peers' regions."""
-        from torch.multiprocessing.reductions import reduce_tensor
-
+        """Exchange the CUDA IPC handles of every slot's symmetric region (host side, once) and map the peers' regions."""
         e = self.eng
         torch.cuda.synchronize(e.device)
-        mine = [reduce_tensor(s.sym) for s in self.slots]
         everyone = [None] * self.world
-        self.dist.all_gather_object(everyone, mine, group=self.group)
-        with torch.cuda.device(e.device):
-            for i, s in enumerate(self.slots):
-                s.peer_tensors = [s.sym if r == self.rank else everyone[r][i][0](*everyone[r][i][1]) for r in range(self.world)]
-                p = _lib.Peers()
-                p.n_peers, p.my_rank = self.world, self.rank
-                for r, t in enumerate(s.peer_tensors):
-                    _lib.check(e.lib.t2p_enable_peer_access(t.device.index), "enable_peer_access")
-                    p.base[r] = t.data_ptr()
-                s.peers = p
+        self.dist.all_gather_object(everyone, [s.sym_buf.handle for s in self.slots], group=self.group)
+        for i, s in enumerate(self.slots):
+            p = _lib.Peers()
+            p.n_peers, p.my_rank = self.world, self.rank
+            for r in range(self.world):
+                p.base[r] = s.sym_buf.ptr if r == self.rank else s.sym_buf.open_peer(everyone[r][i])
+            s.peers = p
         self.dist.barrier(group=self.group)  # nobody pushes before every rank has mapped every region
+
+    def close(self):
+        """Unmap the peers' regions and free the own ones (collective: call on every rank before the process group dies)."""
+        if self.exchange == "p2p":
+            torch.cuda.synchronize(self.eng.device)
+            self.dist.barrier(group=self.group)
+            for s in self.slots:
+                s.graphs = {}
+                s.q_all = s.mine = s.flags = s.sym = None
+                s.sym_buf.close()
 
     def _topk_all(self, s, db):
         e, R = self.eng, self.world

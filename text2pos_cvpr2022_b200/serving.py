@@ -443,6 +443,9 @@ class ShardedOnlineRetrievalEngine:
         for i in range(self.eng.depth):
             self.capture(key, db, slot=i)
 
+    def replay(self, key=0, slot: int = 0):
+        self.slots[slot].graphs[key].replay()
+
     def _enqueue_query(self, slot: int, descriptions, graph_key=None):
         e, s = self.eng, self.slots[slot]
         on_device = e._stage(descriptions, slot)

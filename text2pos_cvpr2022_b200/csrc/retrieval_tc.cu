@@ -324,17 +324,29 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
     if (lane == 0 && ml) atomicMax(&sm->m_last, ml);
   }
 
-  // ---- pre-filter: tau0 = NC-th largest list head; at least NC keys are >= tau0, typically only a few more ----------
-  const bool fast = nsrc <= SEL_THREADS && nsrc >= NC;
+  // ---- pre-filter: a threshold tau0 with at least NC keys >= tau0 and typically only a few more.  List heads are dealt
+  // round-robin to the 8 warps; each warp finds its NC/8-th largest head with a few redux rounds (removing all copies of
+  // the current maximum per round keeps ">= NC/8 heads of this warp are >= the result" true under ties), tau0 = the
+  // minimum over the warps.  O(NC/8) per warp instead of ranking every head against every other.
+  constexpr int NW = SEL_THREADS / 32;
+  const bool fast = nsrc <= 2 * SEL_THREADS && nsrc >= NC && (NC % NW) == 0;
   if (fast) {
-    if (tid < nsrc) {
-      const uint32_t mine = keys[tid * KP];
-      int r = 0;
-      for (int j = 0; j < nsrc; ++j) {
-        const uint32_t h = keys[j * KP];
-        r += (h > mine || (h == mine && j < tid)) ? 1 : 0;
-      }
-      if (r == NC - 1) sm->tau0 = mine;
+    const int t0 = warp + NW * lane, t1 = t0 + SEL_THREADS;
+    uint32_t v0 = t0 < nsrc ? keys[t0 * KP] : 0u;
+    uint32_t v1 = t1 < nsrc ? keys[t1 * KP] : 0u;
+    uint32_t m = 0u;
+    for (int r = 0; r < NC / NW; ++r) {
+      m = __reduce_max_sync(0xffffffffu, max(v0, v1));
+      v0 = v0 == m ? 0u : v0;
+      v1 = v1 == m ? 0u : v1;
+    }
+    if (lane == 0) sm->wsum[0][warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t t = 0xffffffffu;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t = min(t, sm->wsum[0][w]);
+      sm->tau0 = t;  // 0 if some warp saw fewer than NC/8 non-empty heads: everything survives, the general path decides
     }
     __syncthreads();
   }
@@ -367,8 +379,16 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
   int n_cand = 0;
   bool need_rescan = p.force_rescan != 0;
 
-  if (n_surv <= SEL_SURV_MAX) {
-    // exact selection among the survivors by rank counting: rank = #survivors that sort before (key desc, position asc)
+  if (n_surv <= NC + 8) {
+    // few survivors: every one becomes a candidate (at least NC of them are the NC best keys overall)
+    if (tid < n_surv) {
+      const uint32_t mine = sm->surv_key[tid];
+      sm->cand_key[tid] = mine;
+      sm->cand_row[tid] = row_of(sm->surv_pos[tid], mine);
+    }
+    n_cand = n_surv;
+  } else if (n_surv <= SEL_SURV_MAX) {
+    // exact selection of the NC best survivors by rank counting: rank = #survivors that sort before (key desc, position asc)
     uint32_t drop = 0u;
     if (tid < n_surv) {
       const uint32_t mine = sm->surv_key[tid];
@@ -387,7 +407,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
     }
     drop = __reduce_max_sync(0xffffffffu, drop);
     if (lane == 0 && drop) atomicMax(&sm->below_max, drop);
-    n_cand = min(n_surv, NC);
+    n_cand = NC;
   } else {
     // general path (many sources or dense keys): tau = NC-th largest key by bisection on the key bits
     uint32_t tau = 0u;
@@ -426,31 +446,67 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
   __syncthreads();
 
   if (!need_rescan) {
-    // float64 re-scoring: each warp takes up to 8 candidates (f = warp + 8 j) and keeps all their loads in flight
+    // float64 re-scoring: each warp takes up to 8 candidates (f = warp + 8 j).  D % 128 == 0 (the tensor path needs
+    // D % 32 == 0; 128, 256 are the model sizes): a row is read as float4, 32 lanes x D/128 loads, and ALL loads of all the
+    // warp's candidates are issued before the first use -- one L2/DRAM round trip instead of one per 32 channels.
     {
-      constexpr int NW = SEL_THREADS / 32, PER = SEL_CAND_MAX / NW;
-      double acc[PER];
-      const float* rows[PER];
+      constexpr int NWS = SEL_THREADS / 32, PER = SEL_CAND_MAX / NWS;
+      if ((D & 127) == 0 && D <= 256) {
+        const int nv = D >> 7;  // float4 loads per lane and row: 1 or 2
+        float4 v[PER][2];
 #pragma unroll
-      for (int jx = 0; jx < PER; ++jx) {
-        const int f = warp + NW * jx;
-        acc[jx] = 0.0;
-        rows[jx] = db + (size_t)sm->cand_row[f < n_cand ? f : 0] * D;
-      }
-      for (int ch = lane; ch < D; ch += 32) {
-        const double qv = (double)qs[ch];
+        for (int jx = 0; jx < PER; ++jx) {
+          const int f = warp + NWS * jx;
+          const float4* row = reinterpret_cast<const float4*>(db + (size_t)sm->cand_row[f < n_cand ? f : 0] * D);
 #pragma unroll
-        for (int jx = 0; jx < PER; ++jx)
-          if (warp + NW * jx < n_cand) acc[jx] = fma(qv, (double)__ldg(rows[jx] + ch), acc[jx]);
-      }
+          for (int c = 0; c < 2; ++c)
+            v[jx][c] = (f < n_cand && c < nv) ? __ldg(row + lane + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4* q4 = reinterpret_cast<const float4*>(qs);
+        float4 qv[2];
 #pragma unroll
-      for (int jx = 0; jx < PER; ++jx) {
-        const int f = warp + NW * jx;
-        if (f < n_cand) {  // warp-uniform
-          double a = acc[jx];
+        for (int c = 0; c < 2; ++c) qv[c] = c < nv ? q4[lane + 32 * c] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (lane == 0) sm->cand_score[f] = a;
+        for (int jx = 0; jx < PER; ++jx) {
+          const int f = warp + NWS * jx;
+          if (f < n_cand) {  // warp-uniform
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              a = fma((double)qv[c].x, (double)v[jx][c].x, a);
+              a = fma((double)qv[c].y, (double)v[jx][c].y, a);
+              a = fma((double)qv[c].z, (double)v[jx][c].z, a);
+              a = fma((double)qv[c].w, (double)v[jx][c].w, a);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) sm->cand_score[f] = a;
+          }
+        }
+      } else {
+        double acc[PER];
+        const float* rows[PER];
+#pragma unroll
+        for (int jx = 0; jx < PER; ++jx) {
+          const int f = warp + NWS * jx;
+          acc[jx] = 0.0;
+          rows[jx] = db + (size_t)sm->cand_row[f < n_cand ? f : 0] * D;
+        }
+        for (int ch = lane; ch < D; ch += 32) {
+          const double qv = (double)qs[ch];
+#pragma unroll
+          for (int jx = 0; jx < PER; ++jx)
+            if (warp + NWS * jx < n_cand) acc[jx] = fma(qv, (double)__ldg(rows[jx] + ch), acc[jx]);
+        }
+#pragma unroll
+        for (int jx = 0; jx < PER; ++jx) {
+          const int f = warp + NWS * jx;
+          if (f < n_cand) {  // warp-uniform
+            double a = acc[jx];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) sm->cand_score[f] = a;
+          }
         }
       }
     }

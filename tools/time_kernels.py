@@ -63,6 +63,16 @@ def main():
         print(f"lstm path {path}: {us:8.1f} us / batch of 64 x {t.shape[1]} tokens   max|diff vs path 2| = {err:.2e}", flush=True)
     eng.lstm_desc.path = 0
     eng.enqueue_encode(d_tok, d_len)
+    # top-k at the per-rank shapes of the data-parallel sharded engine: R*64 queries against a 12,500-row shard
+    from text2pos_cvpr2022_b200.retrieval import retrieve_topk, db_row_norm2_max
+    db = syn.synth_db_embeddings(100, 12500, 256).to(dev)
+    copies = [db.clone() for _ in range(32)]
+    nm = db_row_norm2_max(db)
+    ws = _lib.Workspace()
+    for B in (64, 128, 256, 512):
+        q = syn.synth_query_embeddings(3, B, 256).to(dev)
+        us = time_cuda(lambda i=0: retrieve_topk(q, copies[i % 32], 10, 0, ws, nm), args.iters)
+        print(f"topk B={B:4d} N=12500: {us:8.1f} us (incl. 2 torch.empty per call)", flush=True)
     for n in (10000, 12500, 100000):
         db = syn.synth_db_embeddings(100, n, 256).to(dev)
         ncopies = max(2, int(400e6 // (n * 1024)) + 1)

@@ -217,7 +217,8 @@ def main_b200(args):
     copies = [base] + [base.clone() for _ in range(N_DB_COPIES - 1)]
 
     depth = max(1, args.depth)  # batches in flight (one stream per slot)
-    eng = OnlineRetrievalEngine(model, base, k=TOPK, max_batch=B_QUERIES, max_tokens=T, idx_base=lo, depth=depth)
+    eng = OnlineRetrievalEngine(model, base, k=TOPK, max_batch=B_QUERIES, max_tokens=T, idx_base=lo, depth=depth,
+                                lstm_clusters=args.lstm_clusters)
     sharded = ShardedOnlineRetrievalEngine(eng, exchange=args.exchange) if world > 1 else None
     user = sharded if sharded is not None else eng
     q_per_step = B_QUERIES * world  # whole job
@@ -412,7 +413,7 @@ def main_b200(args):
                    "weights": "random-init", "parallelism": par},
         "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": (OnlineRetrievalEngine.KERNELS_PER_STEP + ((5 if args.exchange == "p2p" else 1) if world > 1 else 0)) * K * world,
-        "pipeline": {"depth": depth, "serial_ms_per_step": serial_ms_step, "serial_value": q_per_step / (serial_ms_step * 1e-3),
+        "pipeline": {"depth": depth, "lstm_clusters_per_direction": eng.lstm_desc.max_groups or 7, "serial_ms_per_step": serial_ms_step, "serial_value": q_per_step / (serial_ms_step * 1e-3),
                      "cuda_graphs": graphs,
                      "note": "value/ms_per_step: `depth` batches in flight on separate streams, one CUDA-graph replay per step; "
                              "roofline kernel times: serial pass of direct launches"},
@@ -431,8 +432,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lstm-clusters", type=int, default=None, help="LSTM clusters per direction (default: 2 if depth > 1 else 7)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange: own peer-memory kernels or NCCL")
-    ap.add_argument("--depth", type=int, default=4, help="batches in flight (one stream per slot)")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight (one stream per slot)")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

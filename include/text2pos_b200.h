@@ -218,7 +218,8 @@ typedef struct {
   int32_t path;        /* 0 = auto (tensor-core kernel when H == 256, else register kernel, else cluster kernel);
                           1 = shared-memory cluster kernel, 2 = register-resident kernel, 3 = tensor-core kernel */
   int32_t max_groups;  /* tensor-core kernel: clusters per direction a batch is spread over, 1..7; 0 = 7 (lowest latency).
-                          A pipelined server uses 4: ~10% more latency per batch, ~40% less SM-time */
+                          A cluster takes up to 32 sequences (two ping-pong groups of <= 16); a pipelined server uses 2
+                          clusters per direction for 64 queries: a little more latency per batch, about half the SM-time */
 } t2p_lstm_desc;
 
 /* Host-side tokeniser with the reference's rules (models/modules.py:60-72): '.' and ',' removed, lower-cased, split on

@@ -58,6 +58,30 @@ def test_language_encoder_every_kernel_path_H256(path, B):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("max_groups,B", [(2, 64), (1, 64), (1, 32), (1, 19), (3, 64), (2, 130), (4, 64), (1, 17), (2, 3)])
+def test_language_encoder_tensor_core_cluster_geometries(max_groups, B):
+    """tcgen05 kernel, every launch geometry: clusters of <= 16 sequences (one group), clusters of 17..32 sequences run as
+    two ping-pong groups (uneven halves, different longest rows per group), and waves of clusters for large batches."""
+    enc = LanguageEncoder(syn.known_words(), 256, bi_dir=True)
+    syn.randomize_module_(enc, 78)
+    sd = cpu_state_dict(enc)
+    enc = enc.cuda().eval()
+    texts = syn.synth_queries(400 + B, B, 6)
+    texts[0] = "north"  # length 1
+    if B > 20:
+        texts[20] = "the pose is north of a gray building " * 7  # 56 tokens: lands in the second group of a 32-wide cluster
+    texts[B - 1] = "west of a green wall"
+    _, desc = enc.t2p_packed()
+    desc.path, desc.max_groups = 3, max_groups
+    try:
+        out = enc(texts)
+    finally:
+        desc.path, desc.max_groups = 0, 0
+    tokens, lengths = oracle.text.tokenize(texts, enc.known_words)
+    ref = oracle.text.language_encoder(sd, "", tokens, lengths)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5, rtol=1e-4)
+
+
 def test_encode_text_normalised(coarse_model):
     texts = syn.synth_queries(5, 64)
     out = coarse_model.encode_text(texts)

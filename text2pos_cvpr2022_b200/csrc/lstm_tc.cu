@@ -39,14 +39,14 @@ constexpr int LTC_THREADS = 32 * (LTC_EPI_WARPS + 1);  // warps 0-7: epilogue, w
 constexpr int LTC_W_HALFS = 2 * 128 * 256;      // per (direction, rank): hi|lo x 128 rows x 256 k fp16 = 128 KB
 constexpr int LTC_HB_PART = 4 * LTC_NS * 128;   // one of {hi, lo}: 4 K-chunks x 16 rows x 128 bytes = 8 KB
 constexpr int LTC_HB_BUF = 2 * LTC_HB_PART;     // hi + lo
-constexpr int LTC_TMEM_COLS = 512;              // [0,128) W hi, [128,256) W lo, [256,272) accumulator
+constexpr int LTC_TMEM_COLS = 512;              // [0,128) W hi, [128,256) W lo, [256,272) / [272,288) accumulators of the two groups
 constexpr int LTC_D_COL = 256;
 constexpr float LTC_UNSCALE = 1.f / 4096.f;     // 2^-8 (W) * 2^-4 (h)
 constexpr float LTC_HSCALE = 16.f;
 
 struct LtcBars {
-  uint64_t h_bar[2];
-  uint64_t mma_bar;
+  uint64_t h_bar[2][2];  // [group][buffer]
+  uint64_t mma_bar[2];   // [group]
   uint32_t tmem_slot;
 };
 
@@ -120,40 +120,53 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
                const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (LTC_W_HALFS per slice)
                const int32_t* __restrict__ tokens, const int32_t* __restrict__ lengths, int B, int T, int V,
                float* __restrict__ hfinal, int ns) {
+  // ns = sequences of this cluster (<= 32).  ns <= 16: one group.  ns > 16: two groups of ceil(ns/2) / floor(ns/2) sequences
+  // that share the W_hh slice in tensor memory and take turns ("ping-pong"): while the h of one group crosses the
+  // SM-to-SM network, the other group's MMAs and cell updates run -- the step stays network-bound, but the network is
+  // busy all the time, so a batch needs half the SM-time.
   // declared 1024-byte aligned (128-byte swizzle atoms): keeps the shared address space visible to the compiler, so the
   // token / staging accesses compile to LDS/STS instead of generic loads
   extern __shared__ __align__(1024) uint8_t ltc_raw[];
   uint8_t* base = ltc_raw;
   if ((smem_u32(base) & 1023u) != 0u) __trap();
-  uint8_t* hb_smem = base;                                   // [2 buffers][hi|lo][4 chunks][16 x 128 B]
-  uint8_t* stage_smem = hb_smem + 2 * LTC_HB_BUF;            // [8 warps][hi|lo][8 seqs][8 units] fp16 = 256 B each
+  const int NG = ns > LTC_NS ? 2 : 1;
+  const int nsg[2] = {NG == 2 ? (ns + 1) / 2 : ns, NG == 2 ? ns / 2 : 0};  // sequences per group
+  uint8_t* hb_smem = base;                                   // [group][2 buffers][hi|lo][4 chunks][16 x 128 B]
+  uint8_t* stage_smem = hb_smem + 2 * 2 * LTC_HB_BUF;        // [8 warps][hi|lo][8 seqs][8 units] fp16 = 256 B each
   LtcBars* bars = reinterpret_cast<LtcBars*>(stage_smem + LTC_EPI_WARPS * 256);
-  int* tok = reinterpret_cast<int*>(bars + 1);               // [NS][T]
-  int* len = tok + LTC_NS * T;                               // [NS]
+  int* tok = reinterpret_cast<int*>(bars + 1);               // [group][NS][T]
+  int* len = tok + 2 * LTC_NS * T;                           // [group][NS]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / LTC_CS;
-  const int dir = cid & 1, group = cid >> 1;
+  const int dir = cid & 1, cgroup = cid >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = group * ns;  // the group's sequences are b0 .. b0 + ns - 1 (ns <= 16; UMMA columns >= ns are padding)
+  const int b0g[2] = {cgroup * ns, cgroup * ns + nsg[0]};  // first batch row of each group (UMMA columns >= nsg are padding)
   const int u0 = rank * 32;
-  const uint32_t STEP_BYTES = (uint32_t)ns * 1024u;  // h of the group's ns real sequences: 256 units x (hi + lo) fp16 each
+  // h of a group's real sequences per step: 256 units x (hi + lo) fp16 each
+  const uint32_t step_bytes[2] = {(uint32_t)nsg[0] * 1024u, (uint32_t)nsg[1] * 1024u};
 
-  for (int t = tid; t < 2 * LTC_HB_BUF / 16; t += LTC_THREADS) reinterpret_cast<uint4*>(hb_smem)[t] = make_uint4(0, 0, 0, 0);
-  for (int t = tid; t < LTC_NS * T; t += LTC_THREADS) {
-    const int b = t / T, tt = t - b * T;
-    const int v = (b < ns && b0 + b < B) ? tokens[(size_t)(b0 + b) * T + tt] : 0;
+  for (int t = tid; t < 2 * 2 * LTC_HB_BUF / 16; t += LTC_THREADS) reinterpret_cast<uint4*>(hb_smem)[t] = make_uint4(0, 0, 0, 0);
+  for (int t = tid; t < 2 * LTC_NS * T; t += LTC_THREADS) {
+    const int g = t / (LTC_NS * T), r = t - g * (LTC_NS * T);
+    const int b = r / T, tt = r - b * T;
+    const int v = (b < nsg[g] && b0g[g] + b < B) ? tokens[(size_t)(b0g[g] + b) * T + tt] : 0;
     tok[t] = (v < 0 || v >= V) ? 0 : v;
   }
-  if (tid < LTC_NS) len[tid] = (tid < ns && b0 + tid < B) ? min(max(lengths[b0 + tid], 0), T) : 0;
+  if (tid < 2 * LTC_NS) {
+    const int g = tid / LTC_NS, b = tid - g * LTC_NS;
+    len[tid] = (b < nsg[g] && b0g[g] + b < B) ? min(max(lengths[b0g[g] + b], 0), T) : 0;
+  }
   if (tid == 0) {
-    mbar_init(&bars->h_bar[0], 1);
-    mbar_init(&bars->h_bar[1], 1);
-    mbar_init(&bars->mma_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->h_bar[0][0] + i, 1);
+    mbar_init(&bars->mma_bar[0], 1);
+    mbar_init(&bars->mma_bar[1], 1);
     mbar_fence_init();
-    mbar_expect_tx(&bars->h_bar[0], STEP_BYTES);  // armed for their first use (steps 2 and 1)
-    mbar_expect_tx(&bars->h_bar[1], STEP_BYTES);
+    for (int g = 0; g < 2; ++g) {
+      mbar_expect_tx(&bars->h_bar[g][0], step_bytes[g]);  // armed for their first use (steps 2 and 1)
+      mbar_expect_tx(&bars->h_bar[g][1], step_bytes[g]);
+    }
   }
   if (warp == LTC_EPI_WARPS) tmem_alloc<LTC_TMEM_COLS>(&bars->tmem_slot);
   fence_proxy_async_smem();  // the zero-filled h buffers (generic stores) will be read by the tensor core
@@ -161,9 +174,13 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_slot;
-  int max_len = 0;
+  int max_len[2] = {0, 0};
 #pragma unroll
-  for (int b = 0; b < LTC_NS; ++b) max_len = max(max_len, len[b]);
+  for (int b = 0; b < LTC_NS; ++b) {
+    max_len[0] = max(max_len[0], len[b]);
+    max_len[1] = max(max_len[1], len[LTC_NS + b]);
+  }
+  const int steps = max(max_len[0], max_len[1]);
 
   if (warp < LTC_EPI_WARPS) {
     // W_hh slice -> tensor memory: thread = row m (TMEM lane 32*(warp%4) + lane), warps 0-3 write the hi part, 4-7 the lo
@@ -189,61 +206,70 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
   if (warp == LTC_EPI_WARPS) {
-    // ===== control warp (warp-uniform loop; one elected lane issues): per step wait(h) -> MMAs -> commit.  One barrier
-    // per buffer: splitting it per source CTA to start the MMAs of early slices sooner was measured SLOWER (8 waits +
-    // 8 proxy fences per step cost more than the 48 MMAs they would hide). =====
+    // ===== control warp (warp-uniform loop; one elected lane issues): per step and group wait(h) -> MMAs -> commit.  One
+    // barrier per buffer: splitting it per source CTA to start the MMAs of early slices sooner was measured SLOWER (8
+    // waits + 8 proxy fences per step cost more than the 48 MMAs they would hide). =====
     const uint32_t idesc = umma_idesc_f16(128, LTC_NS);
     const uint32_t hb_addr = smem_u32(hb_smem);
-    const uint32_t tmem_d = tmem_base + LTC_D_COL;
-    for (int step = 0; step < max_len; ++step) {
+    for (int step = 0; step < steps; ++step) {
       const int cur = step & 1;
-      if (step > 0) {
-        mbar_wait(&bars->h_bar[cur], (uint32_t)(((step - 1) >> 1) & 1));
-        if (lane == 0) mbar_expect_tx(&bars->h_bar[cur], STEP_BYTES);  // re-arm for step + 2
-        fence_proxy_async_smem();  // h arrived through the generic proxy (st.async), the UMMA reads via the async proxy
-      }
-      tc_fence_after_sync();
-      if (ltc_elect_one()) {
-        const uint32_t hb = hb_addr + cur * LTC_HB_BUF;
-        bool acc = false;
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {  // W_hi*h_hi, W_hi*h_lo, W_lo*h_hi
-          const uint32_t a_col = tmem_base + (prod == 2 ? 128 : 0);
-          const uint32_t ha = hb + (prod == 1 ? LTC_HB_PART : 0);
+      for (int g = 0; g < 2; ++g) {
+        if (step >= max_len[g]) continue;  // warp-uniform
+        if (step > 0) {
+          mbar_wait(&bars->h_bar[g][cur], (uint32_t)(((step - 1) >> 1) & 1));
+          if (lane == 0) mbar_expect_tx(&bars->h_bar[g][cur], step_bytes[g]);  // re-arm for step + 2
+          fence_proxy_async_smem();  // h arrived through the generic proxy (st.async), the UMMA reads via the async proxy
+        }
+        tc_fence_after_sync();
+        if (ltc_elect_one()) {
+          const uint32_t hb = hb_addr + (g * 2 + cur) * LTC_HB_BUF;
+          const uint32_t tmem_d = tmem_base + LTC_D_COL + g * LTC_NS;
+          bool acc = false;
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
-            const uint64_t b_desc = umma_desc_sw128_kmajor(ha + kc * (LTC_NS * 128));
+          for (int prod = 0; prod < 3; ++prod) {  // W_hi*h_hi, W_hi*h_lo, W_lo*h_hi
+            const uint32_t a_col = tmem_base + (prod == 2 ? 128 : 0);
+            const uint32_t ha = hb + (prod == 1 ? LTC_HB_PART : 0);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {  // K = 16 fp16 per instruction: 8 TMEM columns of A, 32 bytes of B
-              umma_f16_ts(tmem_d, a_col + (kc * 4 + ks) * 8, b_desc + 2 * ks, idesc, acc);
-              acc = true;
+            for (int kc = 0; kc < 4; ++kc) {
+              const uint64_t b_desc = umma_desc_sw128_kmajor(ha + kc * (LTC_NS * 128));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // K = 16 fp16 per instruction: 8 TMEM columns of A, 32 bytes of B
+                umma_f16_ts(tmem_d, a_col + (kc * 4 + ks) * 8, b_desc + 2 * ks, idesc, acc);
+                acc = true;
+              }
             }
           }
+          umma_commit(&bars->mma_bar[g]);
         }
-        umma_commit(&bars->mma_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===== epilogue warps: TMEM lane m = 32*q + lane  <->  unit 8*q + lane/4, gate lane%4; columns = sequences =====
     const int q = warp & 3, hf = warp >> 2;
-    const int g = lane & 3, jj = lane >> 2;
-    const bool gb0 = (g & 1) != 0, gb1 = (g & 2) != 0;
+    const int g4 = lane & 3, jj = lane >> 2;
+    const bool gb0 = (g4 & 1) != 0, gb1 = (g4 & 2) != 0;
     const int unit = u0 + 8 * q + jj;
-    const int s0 = 8 * hf + 2 * g;  // this thread finalises sequences s0, s0 + 1 of the group
-    int my_len[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) my_len[e] = len[s0 + e];
-    float c_state[2] = {0.f, 0.f}, h_state[2] = {0.f, 0.f};
+    const int s0 = 8 * hf + 2 * g4;  // this thread finalises sequences s0, s0 + 1 of each group
+    int my_len[2][2];
+    float c_state[2][2], h_state[2][2];
+    float4 xn[2][2];
     const float4* xp_base = xproj4 + (size_t)dir * V * LTC_H + unit;
-    auto token_at = [&](int e, int step) -> int {
-      const int L = my_len[e];
+    auto token_at = [&](int g, int e, int step) -> int {
+      const int L = my_len[g][e];
       if (step >= L) return 0;
-      return tok[(s0 + e) * T + (dir ? (L - 1 - step) : step)];
+      return tok[(g * LTC_NS + s0 + e) * T + (dir ? (L - 1 - step) : step)];
     };
-    float4 xn[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) xn[e] = __ldg(xp_base + (size_t)token_at(e, 0) * LTC_H);
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        my_len[g][e] = len[g * LTC_NS + s0 + e];
+        c_state[g][e] = 0.f;
+        h_state[g][e] = 0.f;
+        xn[g][e] = __ldg(xp_base + (size_t)token_at(g, e, 0) * LTC_H);
+      }
     // staging: this warp's [hi|lo][8 seqs][8 units] fp16; lane l ships chunk (part = (l%16)/8, seq = 8*hf + l%8) to four
     // CTAs: lanes 0-15 to rank+1..rank+4, lanes 16-31 to rank, rank+5..rank+7 (no two CTAs target the same peer at once)
     __half* stage = reinterpret_cast<__half*>(stage_smem + warp * 256);
@@ -252,90 +278,95 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     const int k0 = u0 + 8 * q;
     const uint32_t ship_off = (uint32_t)(ship_part * LTC_HB_PART + (k0 >> 6) * (LTC_NS * 128) + ship_seq * 128 +
                                          ((((k0 & 63) >> 3) ^ (ship_seq & 7)) << 4));
-    // cluster-mapped addresses of this lane's chunk slot (buffer 0) and of h_bar[0] in its four destination CTAs
+    // cluster-mapped addresses of this lane's chunk slot (group 0, buffer 0) and of h_bar[0][0] in its four destination CTAs
     uint32_t rdst[4], rbar[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int dst_rank = (lane < 16) ? (rank + 1 + r) : (r == 0 ? rank : rank + 4 + r);
       rdst[r] = ltc_map_rank(smem_u32(hb_smem) + ship_off, (uint32_t)(dst_rank & (LTC_CS - 1)));
-      rbar[r] = ltc_map_rank(smem_u32(&bars->h_bar[0]), (uint32_t)(dst_rank & (LTC_CS - 1)));
+      rbar[r] = ltc_map_rank(smem_u32(&bars->h_bar[0][0]), (uint32_t)(dst_rank & (LTC_CS - 1)));
     }
     const uint32_t tmem_src = tmem_base + ((uint32_t)(q * 32) << 16) + LTC_D_COL + 8 * hf;
 
-    for (int step = 0; step < max_len; ++step) {
+    for (int step = 0; step < steps; ++step) {
       const int nxt = (step + 1) & 1;
-      float4 xg[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) xg[e] = xn[e];
-      if (step + 1 < max_len) {
+      for (int g = 0; g < 2; ++g) {
+        if (step >= max_len[g]) continue;  // warp-uniform
+        float4 xg[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) xn[e] = __ldg(xp_base + (size_t)token_at(e, step + 1) * LTC_H);
-      }
-      mbar_wait(&bars->mma_bar, (uint32_t)(step & 1));
-      tc_fence_after_sync();
-      uint32_t v[8];
-      tmem_ld_32x8(tmem_src, v);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      // 4x4 block transpose (blocks of 2 sequences) over the 4 lanes of a unit as two butterfly stages (xor 2, xor 1);
-      // every register index is static and every choice a predicated select, so the warp never diverges.  Lane g ends
-      // up with, for its sequences: kk0 = gate g, r0 = gate g^1, kk1 = gate g^2, r1 = gate g^3.
-      float ka[4], ra[4];
+        for (int e = 0; e < 2; ++e) xg[e] = xn[g][e];
+        if (step + 1 < max_len[g]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t keep = gb1 ? v[4 + i] : v[i];
-        const uint32_t send = gb1 ? v[i] : v[4 + i];
-        ka[i] = __uint_as_float(keep);
-        ra[i] = __uint_as_float(__shfl_xor_sync(0xffffffffu, send, 2));
-      }
+          for (int e = 0; e < 2; ++e) xn[g][e] = __ldg(xp_base + (size_t)token_at(g, e, step + 1) * LTC_H);
+        }
+        mbar_wait(&bars->mma_bar[g], (uint32_t)(step & 1));
+        tc_fence_after_sync();
+        uint32_t v[8];
+        tmem_ld_32x8(tmem_src + g * LTC_NS, v);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        // 4x4 block transpose (blocks of 2 sequences) over the 4 lanes of a unit as two butterfly stages (xor 2, xor 1);
+        // every register index is static and every choice a predicated select, so the warp never diverges.  Lane g4 ends
+        // up with, for its sequences: kk0 = gate g4, r0 = gate g4^1, kk1 = gate g4^2, r1 = gate g4^3.
+        float ka[4], ra[4];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float kk0 = gb0 ? ka[2 + e] : ka[e];
-        const float sa = gb0 ? ka[e] : ka[2 + e];
-        const float kk1 = gb0 ? ra[2 + e] : ra[e];
-        const float sb = gb0 ? ra[e] : ra[2 + e];
-        const float r0 = __shfl_xor_sync(0xffffffffu, sa, 1);
-        const float r1 = __shfl_xor_sync(0xffffffffu, sb, 1);
-        const float x = gb0 ? r0 : kk0, y = gb0 ? kk0 : r0, z = gb0 ? r1 : kk1, w = gb0 ? kk1 : r1;
-        const float pre_i = gb1 ? z : x, pre_g = gb1 ? x : z, pre_f = gb1 ? w : y, pre_o = gb1 ? y : w;
-        // cell update for (unit, sequence s0 + e)
-        const float pi = fmaf(pre_i, LTC_UNSCALE, xg[e].x);
-        const float pf = fmaf(pre_f, LTC_UNSCALE, xg[e].y);
-        const float pg_ = fmaf(pre_g, LTC_UNSCALE, xg[e].z);
-        const float po = fmaf(pre_o, LTC_UNSCALE, xg[e].w);
-        const float ig = ltc_sigmoid(pi), fg = ltc_sigmoid(pf), gg = ltc_tanh(pg_), og = ltc_sigmoid(po);
-        const float cn = fmaf(fg, c_state[e], ig * gg);
-        const float hn = og * ltc_tanh(cn);
-        const bool active = step < my_len[e];
-        c_state[e] = active ? cn : c_state[e];
-        h_state[e] = active ? hn : h_state[e];
-      }
-      if (step + 1 < max_len) {
-        // h*2^4 -> fp16 hi/lo, staged as [part][seq-in-half][unit-in-warp]
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t keep = gb1 ? v[4 + i] : v[i];
+          const uint32_t send = gb1 ? v[i] : v[4 + i];
+          ka[i] = __uint_as_float(keep);
+          ra[i] = __uint_as_float(__shfl_xor_sync(0xffffffffu, send, 2));
+        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float hs = h_state[e] * LTC_HSCALE;
-          const __half hi = __float2half_rn(hs);
-          const __half lo = __float2half_rn(hs - __half2float(hi));
-          stage[(0 * 8 + 2 * g + e) * 8 + jj] = hi;
-          stage[(1 * 8 + 2 * g + e) * 8 + jj] = lo;
+          const float kk0 = gb0 ? ka[2 + e] : ka[e];
+          const float sa = gb0 ? ka[e] : ka[2 + e];
+          const float kk1 = gb0 ? ra[2 + e] : ra[e];
+          const float sb = gb0 ? ra[e] : ra[2 + e];
+          const float r0 = __shfl_xor_sync(0xffffffffu, sa, 1);
+          const float r1 = __shfl_xor_sync(0xffffffffu, sb, 1);
+          const float x = gb0 ? r0 : kk0, y = gb0 ? kk0 : r0, z = gb0 ? r1 : kk1, w = gb0 ? kk1 : r1;
+          const float pre_i = gb1 ? z : x, pre_g = gb1 ? x : z, pre_f = gb1 ? w : y, pre_o = gb1 ? y : w;
+          // cell update for (unit, sequence s0 + e)
+          const float pi = fmaf(pre_i, LTC_UNSCALE, xg[e].x);
+          const float pf = fmaf(pre_f, LTC_UNSCALE, xg[e].y);
+          const float pg_ = fmaf(pre_g, LTC_UNSCALE, xg[e].z);
+          const float po = fmaf(pre_o, LTC_UNSCALE, xg[e].w);
+          const float ig = ltc_sigmoid(pi), fg = ltc_sigmoid(pf), gg = ltc_tanh(pg_), og = ltc_sigmoid(po);
+          const float cn = fmaf(fg, c_state[g][e], ig * gg);
+          const float hn = og * ltc_tanh(cn);
+          const bool active = step < my_len[g][e];
+          c_state[g][e] = active ? cn : c_state[g][e];
+          h_state[g][e] = active ? hn : h_state[g][e];
         }
-        __syncwarp();
-        const uint4 chunk = *reinterpret_cast<const uint4*>(stage + (ship_part * 8 + ship_sl) * 8);
-        __syncwarp();  // the staging area is rewritten next step
-        const uint32_t doff = (uint32_t)nxt * LTC_HB_BUF, boff = (uint32_t)nxt * 8u;
+        if (step + 1 < max_len[g]) {
+          // h*2^4 -> fp16 hi/lo, staged as [part][seq-in-half][unit-in-warp]
 #pragma unroll
-        if (ship_seq < ns) {  // rows of padding sequences stay zero
+          for (int e = 0; e < 2; ++e) {
+            const float hs = h_state[g][e] * LTC_HSCALE;
+            const __half hi = __float2half_rn(hs);
+            const __half lo = __float2half_rn(hs - __half2float(hi));
+            stage[(0 * 8 + 2 * g4 + e) * 8 + jj] = hi;
+            stage[(1 * 8 + 2 * g4 + e) * 8 + jj] = lo;
+          }
+          __syncwarp();
+          const uint4 chunk = *reinterpret_cast<const uint4*>(stage + (ship_part * 8 + ship_sl) * 8);
+          __syncwarp();  // the staging area is rewritten by the next group / step
+          const uint32_t doff = (uint32_t)(g * 2 + nxt) * LTC_HB_BUF, boff = (uint32_t)(g * 2 + nxt) * 8u;
+          if (ship_seq < nsg[g]) {  // rows of padding sequences stay zero
 #pragma unroll
-          for (int r = 0; r < 4; ++r) ltc_st_async_v4(rdst[r] + doff, chunk, rbar[r] + boff);
+            for (int r = 0; r < 4; ++r) ltc_st_async_v4(rdst[r] + doff, chunk, rbar[r] + boff);
+          }
         }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int b = b0 + s0 + e;
-      if (s0 + e < ns && b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[e];
-    }
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = b0g[g] + s0 + e;
+        if (s0 + e < nsg[g] && b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[g][e];
+      }
   }
   tc_fence_before_sync();
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // no CTA exits while a peer may still store into it
@@ -345,7 +376,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
 }
 
 size_t lstm_tc_smem_bytes(int T) {
-  return (size_t)2 * LTC_HB_BUF + LTC_EPI_WARPS * 256 + sizeof(LtcBars) + ((size_t)LTC_NS * T + LTC_NS) * sizeof(int) + 64;
+  return (size_t)2 * 2 * LTC_HB_BUF + LTC_EPI_WARPS * 256 + sizeof(LtcBars) + ((size_t)2 * LTC_NS * T + 2 * LTC_NS) * sizeof(int) + 64;
 }
 
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,
@@ -353,20 +384,16 @@ int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* token
   const size_t smem = lstm_tc_smem_bytes(T);
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "lstm_encode: T=%d needs %zu bytes of shared memory", T, smem);
   T2P_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // The step is bound by the SM-to-SM network (every CTA sends and receives 7/8 KB per sequence of its group), so the
-  // batch is spread over as many clusters as B200 co-schedules: at most 15 clusters of 8 CTAs are resident
-  // (launch__cluster_max_active), i.e. 7 groups x 2 directions; larger batches run 16 sequences per cluster in waves.
-  // max_groups < 7 trades ~10% latency for SM-time: a pipelined server packs more batches onto the chip with 4 groups.
-  int groups, ns;
-  if (B <= 7 * LTC_NS) {
-    const int gmax = (max_groups >= 1 && max_groups <= 7) ? max_groups : 7;
-    groups = B < gmax ? B : gmax;
-    ns = (B + groups - 1) / groups;
-    groups = (B + ns - 1) / ns;
-  } else {
-    ns = LTC_NS;
-    groups = (B + LTC_NS - 1) / LTC_NS;
-  }
+  // The step is bound by the SM-to-SM network (every CTA sends and receives 7/8 KB per sequence of its group and step).
+  // Lowest latency (max_groups 0 or 7): spread the batch over as many clusters as B200 co-schedules -- at most 15 clusters
+  // of 8 CTAs are resident (launch__cluster_max_active), i.e. 7 clusters x 2 directions, <= 16 sequences each (one group).
+  // Throughput (max_groups 1..6): fewer clusters with up to 32 sequences each, run as two ping-pong groups that keep the
+  // network busy all the time: ~half the SM-time per batch, which is what a server with several batches in flight wants.
+  const int gmax = (max_groups >= 1 && max_groups <= 7) ? max_groups : 7;
+  int groups = B < gmax ? B : gmax;          // clusters per direction
+  int ns = (B + groups - 1) / groups;        // sequences per cluster
+  if (ns > 2 * LTC_NS) ns = 2 * LTC_NS;      // large batches: waves of clusters
+  groups = (B + ns - 1) / ns;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * 2 * LTC_CS);
   cfg.blockDim = dim3(LTC_THREADS);

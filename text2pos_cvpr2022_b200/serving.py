@@ -58,7 +58,8 @@ class OnlineRetrievalEngine:
     KERNELS_PER_STEP = 5  # tokenize, lstm_tc, lstm_finalize, retrieve_scan_tc, retrieve_select
 
     def __init__(self, model, db: torch.Tensor, k: int = 10, max_batch: int = 64, max_tokens: int = 64,
-                 idx_base: int = 0, cell_ids: Optional[Sequence[str]] = None, depth: int = 1, max_text_bytes: int = 1024):
+                 idx_base: int = 0, cell_ids: Optional[Sequence[str]] = None, depth: int = 1, max_text_bytes: int = 1024,
+                 lstm_clusters: Optional[int] = None):
         self.lib = _lib.load()
         self.model = model
         self.weights, desc = model.t2p_packed()
@@ -73,11 +74,15 @@ class OnlineRetrievalEngine:
         self.vocab.to_device(self.device)
         self.max_text_bytes = int(max_text_bytes)  # average bytes per description the staging buffer is sized for
         self.depth = max(1, int(depth))
-        if self.depth > 1:  # throughput mode: fewer, fuller LSTM clusters per batch so that more batches share the chip
+        # LSTM clusters per direction: default 7 (lowest latency) for a synchronous engine; a pipelined one packs the batch
+        # into 2 clusters of two ping-pong groups each (half the SM-time per batch, so more batches share the chip)
+        if lstm_clusters is None:
+            lstm_clusters = 2 if self.depth > 1 else 0
+        if lstm_clusters:
             import copy
 
             self.lstm_desc = copy.copy(self.lstm_desc)
-            self.lstm_desc.max_groups = 4
+            self.lstm_desc.max_groups = int(lstm_clusters)
         # slot 0 runs on the caller's current stream (query / enqueue_*); further slots own a stream each
         self.slots = [_Slot(self, own_stream=(i > 0 or self.depth > 1)) for i in range(self.depth)]
         self._inflight = collections.deque()

@@ -31,8 +31,8 @@ def test_struct_layouts_match_c():
 #include <stdio.h>
 #include "text2pos_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(t2p_linear_desc), sizeof(t2p_pointnet2_desc), sizeof(t2p_objenc_desc),
-         sizeof(t2p_cellagg_desc), sizeof(t2p_lstm_desc), sizeof(t2p_superglue_desc));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(t2p_linear_desc), sizeof(t2p_pointnet2_desc), sizeof(t2p_objenc_desc),
+         sizeof(t2p_cellagg_desc), sizeof(t2p_lstm_desc), sizeof(t2p_superglue_desc), sizeof(t2p_peers));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -41,7 +41,7 @@ int main(void) {
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    py = [ctypes.sizeof(t) for t in (_lib.LinearDesc, _lib.PointNet2Desc, _lib.ObjEncDesc, _lib.CellAggDesc, _lib.LstmDesc, _lib.SuperGlueDesc)]
+    py = [ctypes.sizeof(t) for t in (_lib.LinearDesc, _lib.PointNet2Desc, _lib.ObjEncDesc, _lib.CellAggDesc, _lib.LstmDesc, _lib.SuperGlueDesc, _lib.Peers)]
     assert sizes == py
 
 

@@ -17,7 +17,7 @@ for a in "$@"; do
   fi
   if [ "$a" = "full" ]; then
     echo "== ncu full (online kernels)"
-    timeout 600 ncu --set full --clock-control none --import-source on -k "regex:lstm|retrieve" --launch-skip 24 --launch-count 8 \
+    timeout 600 ncu --set full --clock-control none --import-source on -k "regex:lstm|retrieve|tokenize" --launch-skip 25 --launch-count 10 \
        -f -o gpurun_out/online_full python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ; echo "ncu full rc=$?"
   fi
 done

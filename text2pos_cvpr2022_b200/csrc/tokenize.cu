@@ -108,11 +108,14 @@ __device__ __forceinline__ int tokd_block_exscan(int v, int* warp_tot, int* tota
 }
 
 // stage: [int32 offsets[n_texts + 1] | padding to 16 bytes | text bytes]; description b = bytes [off[b], off[b+1] - 1)
+constexpr int TOKD_TABLE_SMEM = 12288;  // hash table + word characters staged in shared memory when they fit (the usual case)
+
 __global__ void __launch_bounds__(TOKD_THREADS)
 tokenize_kernel(const uint8_t* __restrict__ stage, int n_texts, int text_base, const t2p_vocab::Entry* __restrict__ table,
-                const char* __restrict__ table_chars, uint32_t mask, int max_tokens, int32_t* __restrict__ tokens,
-                int32_t* __restrict__ lengths) {
+                const char* __restrict__ table_chars, uint32_t mask, uint32_t table_bytes, int max_tokens,
+                int32_t* __restrict__ tokens, int32_t* __restrict__ lengths) {
   __shared__ uint8_t comp[TOKD_MAX_BYTES];  // punctuation removed, lower-cased, separators stored as 0
+  __shared__ __align__(16) uint8_t tab_s[TOKD_TABLE_SMEM];
   __shared__ int warp_tot[TOKD_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int32_t* off = reinterpret_cast<const int32_t*>(stage);
@@ -123,6 +126,14 @@ tokenize_kernel(const uint8_t* __restrict__ stage, int n_texts, int text_base, c
     if (tid == 0) lengths[b] = -1;
     return;
   }
+  // the vocabulary (entries + characters, contiguous on the device) goes to shared memory in the same round trip as the text
+  const bool tab_in_smem = table_bytes <= TOKD_TABLE_SMEM;
+  if (tab_in_smem) {
+    const uint4* src = reinterpret_cast<const uint4*>(table);
+    for (uint32_t t = tid; t < (table_bytes + 15) / 16; t += TOKD_THREADS) reinterpret_cast<uint4*>(tab_s)[t] = __ldg(src + t);
+  }
+  const t2p_vocab::Entry* tab = tab_in_smem ? reinterpret_cast<const t2p_vocab::Entry*>(tab_s) : table;
+  const char* tchars = tab_in_smem ? reinterpret_cast<const char*>(tab_s) + (size_t)(mask + 1) * sizeof(t2p_vocab::Entry) : table_chars;
   const uint8_t* text = stage + text_base + begin;
   // 1. drop '.' and ',', lower-case: each thread owns a contiguous segment
   const int seg = (L + TOKD_THREADS - 1) / TOKD_THREADS;
@@ -153,11 +164,11 @@ tokenize_kernel(const uint8_t* __restrict__ stage, int n_texts, int text_base, c
     const uint32_t len = (uint32_t)(e - i);
     int32_t id = 0;
     for (uint32_t slot = (uint32_t)h & mask;; slot = (slot + 1) & mask) {
-      const t2p_vocab::Entry en = table[slot];
+      const t2p_vocab::Entry en = tab[slot];
       if (en.len == 0) break;
       if (en.hash == h && en.len == len) {
         bool same = true;
-        for (uint32_t j = 0; j < len; ++j) same = same && (uint8_t)table_chars[en.off + j] == comp[i + j];
+        for (uint32_t j = 0; j < len; ++j) same = same && (uint8_t)tchars[en.off + j] == comp[i + j];
         if (same) {
           id = en.id;
           break;
@@ -264,7 +275,7 @@ int t2p_vocab_to_device(t2p_vocab* v) {
   }
   const size_t tbytes = v->table.size() * sizeof(t2p_vocab::Entry);
   void* d = nullptr;
-  T2P_CUDA(cudaMalloc(&d, tbytes + v->chars.size() + 16));
+  T2P_CUDA(cudaMalloc(&d, tbytes + v->chars.size() + 32));
   cudaError_t e = cudaMemcpy(d, v->table.data(), tbytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !v->chars.empty())
     e = cudaMemcpy(static_cast<char*>(d) + tbytes, v->chars.data(), v->chars.size(), cudaMemcpyHostToDevice);
@@ -321,8 +332,10 @@ int t2p_tokenize_device(const t2p_vocab* v, const void* d_stage, int n_texts, in
   const int text_base = (int)t2p::align_up((size_t)(n_texts + 1) * sizeof(int32_t), 16);
   const t2p_vocab::Entry* table = static_cast<const t2p_vocab::Entry*>(v->d_table);
   const char* chars = static_cast<const char*>(v->d_table) + v->table.size() * sizeof(t2p_vocab::Entry);
+  const uint32_t table_bytes = (uint32_t)(v->table.size() * sizeof(t2p_vocab::Entry) + v->chars.size());
   t2p::tokenize_kernel<<<n_texts, t2p::TOKD_THREADS, 0, t2p::as_stream(stream)>>>(static_cast<const uint8_t*>(d_stage), n_texts, text_base,
-                                                                                 table, chars, v->mask, max_tokens, d_tokens, d_lengths);
+                                                                                 table, chars, v->mask, table_bytes, max_tokens, d_tokens,
+                                                                                 d_lengths);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

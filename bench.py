@@ -432,9 +432,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lstm-clusters", type=int, default=None, help="LSTM clusters per direction (default: 2 if depth > 1 else 7)")
+    ap.add_argument("--lstm-clusters", type=int, default=None, help="LSTM clusters per direction (default: 7 if depth == 1, 2 if depth < 8, else 1)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange: own peer-memory kernels or NCCL")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight (one stream per slot)")
+    ap.add_argument("--depth", type=int, default=12, help="batches in flight (one stream per slot)")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

@@ -248,6 +248,14 @@ int t2p_stage_texts(const char* texts, size_t total_bytes, int n_texts, void* h_
 int t2p_tokenize_device(const t2p_vocab* v, const void* d_stage, int n_texts, int max_tokens, int32_t* d_tokens,
                         int32_t* d_lengths, t2p_stream stream);
 
+/* Host fast path of the serving engine: t2p_stage_texts (+ its H2D copy), cudaGraphLaunch of the captured step
+ * (`graph_exec` = cudaGraphExec_t), the D2H copy of the `out_bytes` result bytes into pinned memory and cudaEventRecord
+ * (`event` = cudaEvent_t or NULL), all on `stream`, in one call.  *all_ascii = 0: the batch has non-ASCII bytes and NOTHING was
+ * enqueued (the caller tokenises with the Unicode-aware host rules instead). */
+int t2p_serving_submit(const char* texts, size_t total_bytes, int n_texts, void* h_stage, size_t stage_capacity, void* d_stage,
+                       void* graph_exec, const void* d_out, void* h_out, size_t out_bytes, void* event, t2p_stream stream,
+                       size_t* used_bytes, int* all_ascii);
+
 size_t t2p_lstm_encode_workspace(int B, int H);
 /* d_tokens [B,T] int32 (row b valid for t < d_lengths[b]), 1 <= lengths <= T.  d_out [B,H] =
  * 0.5*(h_fwd_final + h_bwd_final), L2-normalised per row if normalize != 0. */

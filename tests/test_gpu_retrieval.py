@@ -100,7 +100,9 @@ def _check_flags(db, q, k, flags, expect_rescans=None, idx_base=0):
 
 
 @pytest.mark.parametrize("B,N,D,k", [(64, 10000, 256, 10), (64, 12500, 256, 10), (1, 128, 256, 10), (130, 3000, 128, 5),
-                                      (7, 50, 32, 10), (3, 5, 64, 10), (64, 100000, 256, 10), (20, 2500, 96, 26), (64, 20000, 256, 1)])
+                                      (7, 50, 32, 10), (3, 5, 64, 10), (64, 100000, 256, 10), (20, 2500, 96, 26), (64, 20000, 256, 1),
+                                      # several query tiles: DB tile resident, queries streamed (sharded-engine shapes) / DB streamed
+                                      (512, 12500, 256, 10), (256, 12500, 256, 10), (300, 777, 64, 10), (200, 40000, 256, 10)])
 def test_tensor_core_path_equals_float64_oracle(B, N, D, k):
     db = syn.synth_db_embeddings(N + D + 1, N, D)
     q = syn.synth_query_embeddings(B + 2, B, D)

@@ -34,19 +34,20 @@ using namespace sm100;
 constexpr int LTC_H = 256;
 constexpr int LTC_CS = 8;        // CTAs per cluster
 constexpr int LTC_NS = 16;       // sequences per cluster (UMMA N)
+constexpr int LTC_MAXG = 4;       // ping-pong groups of <= 16 sequences per cluster
 constexpr int LTC_EPI_WARPS = 8;
 constexpr int LTC_THREADS = 32 * (LTC_EPI_WARPS + 1);  // warps 0-7: epilogue, warp 8: control
 constexpr int LTC_W_HALFS = 2 * 128 * 256;      // per (direction, rank): hi|lo x 128 rows x 256 k fp16 = 128 KB
 constexpr int LTC_HB_PART = 4 * LTC_NS * 128;   // one of {hi, lo}: 4 K-chunks x 16 rows x 128 bytes = 8 KB
 constexpr int LTC_HB_BUF = 2 * LTC_HB_PART;     // hi + lo
-constexpr int LTC_TMEM_COLS = 512;              // [0,128) W hi, [128,256) W lo, [256,272) / [272,288) accumulators of the two groups
+constexpr int LTC_TMEM_COLS = 512;              // [0,128) W hi, [128,256) W lo, [256 + 16 g, +16) accumulator of group g
 constexpr int LTC_D_COL = 256;
 constexpr float LTC_UNSCALE = 1.f / 4096.f;     // 2^-8 (W) * 2^-4 (h)
 constexpr float LTC_HSCALE = 16.f;
 
 struct LtcBars {
-  uint64_t h_bar[2][2];  // [group][buffer]
-  uint64_t mma_bar[2];   // [group]
+  uint64_t h_bar[LTC_MAXG][2];  // [group][buffer]
+  uint64_t mma_bar[LTC_MAXG];   // [group]
   uint32_t tmem_slot;
 };
 
@@ -120,50 +121,57 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
                const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (LTC_W_HALFS per slice)
                const int32_t* __restrict__ tokens, const int32_t* __restrict__ lengths, int B, int T, int V,
                float* __restrict__ hfinal, int ns) {
-  // ns = sequences of this cluster (<= 32).  ns <= 16: one group.  ns > 16: two groups of ceil(ns/2) / floor(ns/2) sequences
-  // that share the W_hh slice in tensor memory and take turns ("ping-pong"): while the h of one group crosses the
-  // SM-to-SM network, the other group's MMAs and cell updates run -- the step stays network-bound, but the network is
-  // busy all the time, so a batch needs half the SM-time.
+  // ns = sequences of this cluster (<= 64), split into NG = ceil(ns/16) groups of <= 16 that share the W_hh slice in tensor
+  // memory and take turns ("ping-pong"): while the h of one group crosses the SM-to-SM network, the MMAs and cell updates
+  // of the others run -- a step stays network-bound, but the network is busy all the time, so a batch needs a fraction of
+  // the SM-time (at the price of latency).
   // declared 1024-byte aligned (128-byte swizzle atoms): keeps the shared address space visible to the compiler, so the
   // token / staging accesses compile to LDS/STS instead of generic loads
   extern __shared__ __align__(1024) uint8_t ltc_raw[];
   uint8_t* base = ltc_raw;
   if ((smem_u32(base) & 1023u) != 0u) __trap();
-  const int NG = ns > LTC_NS ? 2 : 1;
-  const int nsg[2] = {NG == 2 ? (ns + 1) / 2 : ns, NG == 2 ? ns / 2 : 0};  // sequences per group
-  uint8_t* hb_smem = base;                                   // [group][2 buffers][hi|lo][4 chunks][16 x 128 B]
-  uint8_t* stage_smem = hb_smem + 2 * 2 * LTC_HB_BUF;        // [8 warps][hi|lo][8 seqs][8 units] fp16 = 256 B each
+  const int NG = (ns + LTC_NS - 1) / LTC_NS;
+  int nsg[LTC_MAXG], b0g[LTC_MAXG];  // sequences per group (balanced), first batch row of each group
+  uint32_t step_bytes[LTC_MAXG];     // h of a group's real sequences per step: 256 units x (hi + lo) fp16 each
+  uint8_t* hb_smem = base;                                          // [NG groups][2 buffers][hi|lo][4 chunks][16 x 128 B]
+  uint8_t* stage_smem = hb_smem + (size_t)NG * 2 * LTC_HB_BUF;      // [8 warps][hi|lo][8 seqs][8 units] fp16 = 256 B each
   LtcBars* bars = reinterpret_cast<LtcBars*>(stage_smem + LTC_EPI_WARPS * 256);
-  int* tok = reinterpret_cast<int*>(bars + 1);               // [group][NS][T]
-  int* len = tok + 2 * LTC_NS * T;                           // [group][NS]
+  int* tok = reinterpret_cast<int*>(bars + 1);                      // [group][NS][T]
+  int* len = tok + LTC_MAXG * LTC_NS * T;                           // [group][NS]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / LTC_CS;
   const int dir = cid & 1, cgroup = cid >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0g[2] = {cgroup * ns, cgroup * ns + nsg[0]};  // first batch row of each group (UMMA columns >= nsg are padding)
   const int u0 = rank * 32;
-  // h of a group's real sequences per step: 256 units x (hi + lo) fp16 each
-  const uint32_t step_bytes[2] = {(uint32_t)nsg[0] * 1024u, (uint32_t)nsg[1] * 1024u};
+  {
+    int first = cgroup * ns;
+#pragma unroll
+    for (int g = 0; g < LTC_MAXG; ++g) {  // UMMA columns >= nsg[g] are padding
+      nsg[g] = g < NG ? (ns + NG - 1 - g) / NG : 0;
+      b0g[g] = first;
+      first += nsg[g];
+      step_bytes[g] = (uint32_t)nsg[g] * 1024u;
+    }
+  }
 
-  for (int t = tid; t < 2 * 2 * LTC_HB_BUF / 16; t += LTC_THREADS) reinterpret_cast<uint4*>(hb_smem)[t] = make_uint4(0, 0, 0, 0);
-  for (int t = tid; t < 2 * LTC_NS * T; t += LTC_THREADS) {
+  for (int t = tid; t < NG * 2 * LTC_HB_BUF / 16; t += LTC_THREADS) reinterpret_cast<uint4*>(hb_smem)[t] = make_uint4(0, 0, 0, 0);
+  for (int t = tid; t < LTC_MAXG * LTC_NS * T; t += LTC_THREADS) {
     const int g = t / (LTC_NS * T), r = t - g * (LTC_NS * T);
     const int b = r / T, tt = r - b * T;
     const int v = (b < nsg[g] && b0g[g] + b < B) ? tokens[(size_t)(b0g[g] + b) * T + tt] : 0;
     tok[t] = (v < 0 || v >= V) ? 0 : v;
   }
-  if (tid < 2 * LTC_NS) {
+  if (tid < LTC_MAXG * LTC_NS) {
     const int g = tid / LTC_NS, b = tid - g * LTC_NS;
     len[tid] = (b < nsg[g] && b0g[g] + b < B) ? min(max(lengths[b0g[g] + b], 0), T) : 0;
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars->h_bar[0][0] + i, 1);
-    mbar_init(&bars->mma_bar[0], 1);
-    mbar_init(&bars->mma_bar[1], 1);
+    for (int i = 0; i < 2 * LTC_MAXG; ++i) mbar_init(&bars->h_bar[0][0] + i, 1);
+    for (int g = 0; g < LTC_MAXG; ++g) mbar_init(&bars->mma_bar[g], 1);
     mbar_fence_init();
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < LTC_MAXG; ++g) {
       mbar_expect_tx(&bars->h_bar[g][0], step_bytes[g]);  // armed for their first use (steps 2 and 1)
       mbar_expect_tx(&bars->h_bar[g][1], step_bytes[g]);
     }
@@ -174,13 +182,15 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_slot;
-  int max_len[2] = {0, 0};
+  int max_len[LTC_MAXG];
+  int steps = 0;
 #pragma unroll
-  for (int b = 0; b < LTC_NS; ++b) {
-    max_len[0] = max(max_len[0], len[b]);
-    max_len[1] = max(max_len[1], len[LTC_NS + b]);
+  for (int g = 0; g < LTC_MAXG; ++g) {
+    max_len[g] = 0;
+#pragma unroll
+    for (int b = 0; b < LTC_NS; ++b) max_len[g] = max(max_len[g], len[g * LTC_NS + b]);
+    steps = max(steps, max_len[g]);
   }
-  const int steps = max(max_len[0], max_len[1]);
 
   if (warp < LTC_EPI_WARPS) {
     // W_hh slice -> tensor memory: thread = row m (TMEM lane 32*(warp%4) + lane), warps 0-3 write the hi part, 4-7 the lo
@@ -214,7 +224,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     for (int step = 0; step < steps; ++step) {
       const int cur = step & 1;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < LTC_MAXG; ++g) {
         if (step >= max_len[g]) continue;  // warp-uniform
         if (step > 0) {
           mbar_wait(&bars->h_bar[g][cur], (uint32_t)(((step - 1) >> 1) & 1));
@@ -252,9 +262,9 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     const bool gb0 = (g4 & 1) != 0, gb1 = (g4 & 2) != 0;
     const int unit = u0 + 8 * q + jj;
     const int s0 = 8 * hf + 2 * g4;  // this thread finalises sequences s0, s0 + 1 of each group
-    int my_len[2][2];
-    float c_state[2][2], h_state[2][2];
-    float4 xn[2][2];
+    int my_len[LTC_MAXG][2];
+    float c_state[LTC_MAXG][2], h_state[LTC_MAXG][2];
+    float4 xn[LTC_MAXG][2];
     const float4* xp_base = xproj4 + (size_t)dir * V * LTC_H + unit;
     auto token_at = [&](int g, int e, int step) -> int {
       const int L = my_len[g][e];
@@ -262,7 +272,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
       return tok[(g * LTC_NS + s0 + e) * T + (dir ? (L - 1 - step) : step)];
     };
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
+    for (int g = 0; g < LTC_MAXG; ++g)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         my_len[g][e] = len[g * LTC_NS + s0 + e];
@@ -291,7 +301,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     for (int step = 0; step < steps; ++step) {
       const int nxt = (step + 1) & 1;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < LTC_MAXG; ++g) {
         if (step >= max_len[g]) continue;  // warp-uniform
         float4 xg[2];
 #pragma unroll
@@ -361,7 +371,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
       }
     }
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
+    for (int g = 0; g < LTC_MAXG; ++g)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int b = b0g[g] + s0 + e;
@@ -376,7 +386,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
 }
 
 size_t lstm_tc_smem_bytes(int T) {
-  return (size_t)2 * 2 * LTC_HB_BUF + LTC_EPI_WARPS * 256 + sizeof(LtcBars) + ((size_t)2 * LTC_NS * T + 2 * LTC_NS) * sizeof(int) + 64;
+  return (size_t)LTC_MAXG * 2 * LTC_HB_BUF + LTC_EPI_WARPS * 256 + sizeof(LtcBars) + ((size_t)LTC_MAXG * LTC_NS * T + LTC_MAXG * LTC_NS) * sizeof(int) + 64;
 }
 
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,
@@ -387,12 +397,13 @@ int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* token
   // The step is bound by the SM-to-SM network (every CTA sends and receives 7/8 KB per sequence of its group and step).
   // Lowest latency (max_groups 0 or 7): spread the batch over as many clusters as B200 co-schedules -- at most 15 clusters
   // of 8 CTAs are resident (launch__cluster_max_active), i.e. 7 clusters x 2 directions, <= 16 sequences each (one group).
-  // Throughput (max_groups 1..6): fewer clusters with up to 32 sequences each, run as two ping-pong groups that keep the
-  // network busy all the time: ~half the SM-time per batch, which is what a server with several batches in flight wants.
+  // Throughput (max_groups 1..6): fewer clusters with up to 64 sequences each, run as up to four ping-pong groups that keep
+  // the network busy all the time: a fraction of the SM-time per batch, which is what a server with several batches in
+  // flight wants.
   const int gmax = (max_groups >= 1 && max_groups <= 7) ? max_groups : 7;
   int groups = B < gmax ? B : gmax;          // clusters per direction
   int ns = (B + groups - 1) / groups;        // sequences per cluster
-  if (ns > 2 * LTC_NS) ns = 2 * LTC_NS;      // large batches: waves of clusters
+  if (ns > LTC_MAXG * LTC_NS) ns = LTC_MAXG * LTC_NS;  // large batches: waves of clusters
   groups = (B + ns - 1) / ns;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * 2 * LTC_CS);

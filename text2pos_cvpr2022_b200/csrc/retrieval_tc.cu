@@ -95,6 +95,9 @@ struct ScanParams {
   int nb_bits;     // width of the local-row field of the keys
   int dup;         // B <= 64: the query tile is loaded twice (TMEM lanes 64..127 mirror 0..63) and the two halves of
                    // the epilogue warps split the columns of every tile; they write separate key lists (2G sources)
+  int qstream;     // B > 128 and one DB tile per CTA: the DB tile stays resident (q_pitch = its chunk pitch) and the QUERY
+                   // tiles stream through the ring (st_pitch = 16 KB); one key list per (query, CTA) and query tile
+  int qtiles;
 };
 
 template <int KP>
@@ -114,7 +117,8 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const int q0 = blockIdx.y * TC_QM;
   const int tile_n = p.tile_n;
   const int tiles = (p.N + tile_n - 1) / tile_n;
-  const int my_tiles = (tiles - c + G - 1) / G;  // host guarantees c < tiles
+  // iterations of the pipeline: DB tiles of this CTA (query tile resident) or query tiles (qstream: DB tile resident)
+  const int my_tiles = p.qstream ? p.qtiles : (tiles - c + G - 1) / G;  // host guarantees c < tiles
 
   if (threadIdx.x == 0) {
     mbar_init(&sm->q_full, 1);
@@ -139,21 +143,35 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_db);
-      const int q_copies = p.dup ? 2 : 1;
-      mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_copies * p.q_box_rows * 128));
-      for (int kc = 0; kc < nch; ++kc) {
-        tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_q, kc * 32, q0, &sm->q_full);
-        if (p.dup) tma_load_2d(q_smem + (size_t)kc * p.q_pitch + 64 * 128, &tmap_q, kc * 32, q0, &sm->q_full);
-      }
       int stage = 0;
       uint32_t ph = 0;
-      for (int lt = 0; lt < my_tiles; ++lt) {
-        const int row0 = (c + lt * G) * tile_n;
+      if (p.qstream) {
+        // resident operand = this CTA's DB tile (all K chunks), streamed operand = the query tiles
+        mbar_expect_tx(&sm->q_full, (uint32_t)(nch * p.db_box_rows * 128));
+        for (int kc = 0; kc < nch; ++kc) tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_db, kc * 32, c * tile_n, &sm->q_full);
+        for (int qt = 0; qt < my_tiles; ++qt) {
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&sm->empty[stage], ph ^ 1);
+            mbar_expect_tx(&sm->full[stage], (uint32_t)(p.q_box_rows * 128));
+            tma_load_2d(st_smem + (size_t)stage * p.st_pitch, &tmap_q, kc * 32, qt * TC_QM, &sm->full[stage]);
+            if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          }
+        }
+      } else {
+        const int q_copies = p.dup ? 2 : 1;
+        mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_copies * p.q_box_rows * 128));
         for (int kc = 0; kc < nch; ++kc) {
-          mbar_wait(&sm->empty[stage], ph ^ 1);
-          mbar_expect_tx(&sm->full[stage], (uint32_t)(p.db_box_rows * 128));
-          tma_load_2d(st_smem + (size_t)stage * p.st_pitch, &tmap_db, kc * 32, row0, &sm->full[stage]);
-          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_q, kc * 32, q0, &sm->q_full);
+          if (p.dup) tma_load_2d(q_smem + (size_t)kc * p.q_pitch + 64 * 128, &tmap_q, kc * 32, q0, &sm->q_full);
+        }
+        for (int lt = 0; lt < my_tiles; ++lt) {
+          const int row0 = (c + lt * G) * tile_n;
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&sm->empty[stage], ph ^ 1);
+            mbar_expect_tx(&sm->full[stage], (uint32_t)(p.db_box_rows * 128));
+            tma_load_2d(st_smem + (size_t)stage * p.st_pitch, &tmap_db, kc * 32, row0, &sm->full[stage]);
+            if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -174,8 +192,11 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int kc = 0; kc < nch; ++kc) {
           mbar_wait(&sm->full[stage], ph);
           tc_fence_after_sync();
-          const uint64_t a_desc = umma_desc_sw128_kmajor(q_addr + kc * p.q_pitch);
-          const uint64_t b_desc = umma_desc_sw128_kmajor(st_addr + stage * p.st_pitch);
+          // A = queries (M = 128 TMEM lanes), B = DB rows (N = tile_n columns); which of them is resident depends on the mode
+          const uint64_t res_desc = umma_desc_sw128_kmajor(q_addr + kc * p.q_pitch);
+          const uint64_t str_desc = umma_desc_sw128_kmajor(st_addr + stage * p.st_pitch);
+          const uint64_t a_desc = p.qstream ? str_desc : res_desc;
+          const uint64_t b_desc = p.qstream ? res_desc : str_desc;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
             umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
@@ -191,8 +212,6 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     const int tl = quad * 32 + lane;
     const int half = p.dup ? (tl >> 6) : 0;
-    const int qrow = q0 + (p.dup ? (tl & 63) : tl);
-    const bool warp_active = (q0 + (p.dup ? ((quad & 1) * 32) : quad * 32)) < p.B;
     const uint32_t low_mask = (1u << p.nb_bits) - 1u;
     uint32_t L[KP];
 #pragma unroll
@@ -200,12 +219,19 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int n16 = tile_n >> 4;
     const int ch_begin = (p.dup && half) ? ((n16 + 1) >> 1) : 0;
     const int ch_end = (p.dup && !half) ? ((n16 + 1) >> 1) : n16;
+    const int nsrc = p.dup ? 2 * G : G;
+    const int src = p.dup ? 2 * c + half : c;
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int acc = lt & 1;
+      // qstream: iteration lt is query tile lt against the CTA's single DB tile; otherwise DB tile lt against query tile blockIdx.y
+      const int qbase = p.qstream ? lt * TC_QM : q0;
+      const int qrow = qbase + (p.dup ? (tl & 63) : tl);
+      const bool warp_active = (qbase + (p.dup ? ((quad & 1) * 32) : quad * 32)) < p.B;
+      const int row0 = p.qstream ? c * tile_n : (c + lt * G) * tile_n;
+      const uint32_t local0 = p.qstream ? 0u : (uint32_t)(lt * TC_TILE_MAX);
       mbar_wait(&sm->tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after_sync();
       if (warp_active) {
-        const int row0 = (c + lt * G) * tile_n;
         for (int ch = ch_begin; ch < ch_end; ++ch) {
           uint32_t v[16];
           tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_TILE_MAX + ch * 16, v);
@@ -214,7 +240,7 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           for (int j = 0; j < 16; ++j) {
             const int col = ch * 16 + j;
             const bool ok = row0 + col < p.N;
-            uint32_t x = ok ? score_to_key(__uint_as_float(v[j]), low_mask, (uint32_t)(lt * TC_TILE_MAX + col)) : 0u;
+            uint32_t x = ok ? score_to_key(__uint_as_float(v[j]), low_mask, local0 + (uint32_t)col) : 0u;
             if (__any_sync(0xffffffffu, x > L[KP - 1])) {
 #pragma unroll
               for (int i = 0; i < KP; ++i) {
@@ -228,13 +254,15 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       tc_fence_before_sync();
       mbar_arrive(&sm->tmem_empty[acc]);
-    }
-    if (qrow < p.B && warp_active) {
-      const int nsrc = p.dup ? 2 * G : G;
-      const int src = p.dup ? 2 * c + half : c;
-      uint4* dst = reinterpret_cast<uint4*>(part_keys + ((size_t)qrow * nsrc + src) * KP);
+      if (p.qstream || lt == my_tiles - 1) {  // the list of (query, CTA) is complete: write it (qstream: one per query tile)
+        if (qrow < p.B && warp_active) {
+          uint4* dst = reinterpret_cast<uint4*>(part_keys + ((size_t)qrow * nsrc + src) * KP);
 #pragma unroll
-      for (int i = 0; i < KP / 4; ++i) dst[i] = make_uint4(L[4 * i], L[4 * i + 1], L[4 * i + 2], L[4 * i + 3]);
+          for (int i = 0; i < KP / 4; ++i) dst[i] = make_uint4(L[4 * i], L[4 * i + 1], L[4 * i + 2], L[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < KP; ++i) L[i] = 0u;
+      }
     }
   }
   tc_fence_before_sync();
@@ -278,7 +306,7 @@ struct SelParams {
   int64_t idx_base;
 };
 
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 3)
 retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, const SelParams p,
                        const uint32_t* __restrict__ part_keys, const float* __restrict__ db_norm2_max,
                        double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats) {
@@ -453,34 +481,38 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
       constexpr int NWS = SEL_THREADS / 32, PER = SEL_CAND_MAX / NWS;
       if ((D & 127) == 0 && D <= 256) {
         const int nv = D >> 7;  // float4 loads per lane and row: 1 or 2
-        float4 v[PER][2];
-#pragma unroll
-        for (int jx = 0; jx < PER; ++jx) {
-          const int f = warp + NWS * jx;
-          const float4* row = reinterpret_cast<const float4*>(db + (size_t)sm->cand_row[f < n_cand ? f : 0] * D);
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-            v[jx][c] = (f < n_cand && c < nv) ? __ldg(row + lane + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         const float4* q4 = reinterpret_cast<const float4*>(qs);
         float4 qv[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) qv[c] = c < nv ? q4[lane + 32 * c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int HALF = PER / 2;  // 4 candidates per warp and pass: <= 32 candidates (the usual case) need one pass
+        for (int pass = 0; pass < 2; ++pass) {
+          if (warp + NWS * (pass * HALF) >= n_cand) break;  // warp-uniform
+          float4 v[HALF][2];
 #pragma unroll
-        for (int jx = 0; jx < PER; ++jx) {
-          const int f = warp + NWS * jx;
-          if (f < n_cand) {  // warp-uniform
-            double a = 0.0;
+          for (int jx = 0; jx < HALF; ++jx) {
+            const int f = warp + NWS * (pass * HALF + jx);
+            const float4* row = reinterpret_cast<const float4*>(db + (size_t)sm->cand_row[f < n_cand ? f : 0] * D);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              a = fma((double)qv[c].x, (double)v[jx][c].x, a);
-              a = fma((double)qv[c].y, (double)v[jx][c].y, a);
-              a = fma((double)qv[c].z, (double)v[jx][c].z, a);
-              a = fma((double)qv[c].w, (double)v[jx][c].w, a);
+            for (int c = 0; c < 2; ++c)
+              v[jx][c] = (f < n_cand && c < nv) ? __ldg(row + lane + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int jx = 0; jx < HALF; ++jx) {
+            const int f = warp + NWS * (pass * HALF + jx);
+            if (f < n_cand) {  // warp-uniform
+              double a = 0.0;
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                a = fma((double)qv[c].x, (double)v[jx][c].x, a);
+                a = fma((double)qv[c].y, (double)v[jx][c].y, a);
+                a = fma((double)qv[c].z, (double)v[jx][c].z, a);
+                a = fma((double)qv[c].w, (double)v[jx][c].w, a);
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+              if (lane == 0) sm->cand_score[f] = a;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) sm->cand_score[f] = a;
           }
         }
       } else {
@@ -657,13 +689,21 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
   p.nsrc = p.dup ? 2 * p.G : p.G;
   p.nb_bits = 7 + ceil_log2(p.tiles_per_cta);
   const int nch = D / 32;
-  p.q_pitch = (int)align_up((size_t)(p.dup ? 128 : std::min(TC_QM, B)) * 128, 1024);
-  p.st_pitch = p.tile_n * 128;
+  // several query tiles against a DB that gives every CTA one tile: keep the DB tile resident and stream the queries
+  // (one launch wave, the DB is read once, no per-query-tile prologue)
+  p.qstream = (p.qtiles > 1 && p.tiles_per_cta == 1) ? 1 : 0;
+  if (p.qstream) {
+    p.q_pitch = (int)align_up((size_t)p.tile_n * 128, 1024);  // resident operand: the DB tile
+    p.st_pitch = TC_QM * 128;                                  // streamed operand: one 128-query chunk
+  } else {
+    p.q_pitch = (int)align_up((size_t)(p.dup ? 128 : std::min(TC_QM, B)) * 128, 1024);
+    p.st_pitch = p.tile_n * 128;
+  }
   const size_t fixed = 1024 + (size_t)nch * p.q_pitch + 16384 + sizeof(ScanSmem) + 64;
   const size_t budget = 220 * 1024;
   if (fixed + 2 * (size_t)p.st_pitch > budget) return p;
   p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / p.st_pitch);
-  p.stages = std::min(p.stages, std::max(2, nch * p.tiles_per_cta));
+  p.stages = std::min(p.stages, std::max(2, nch * (p.qstream ? p.qtiles : p.tiles_per_cta)));
   p.scan_smem = fixed + (size_t)p.stages * p.st_pitch;
   p.sel_smem = sizeof(SelSmem) + (size_t)D * 4 + (size_t)p.nsrc * p.KP * 4;
   if (p.sel_smem > 200 * 1024) return p;
@@ -702,11 +742,11 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
   sp.q_box_rows = std::min(p.dup ? 64 : TC_QM, B);
   sp.db_box_rows = std::min(p.tile_n, N);
   sp.q_pitch = p.q_pitch; sp.st_pitch = p.st_pitch; sp.stages = p.stages;
-  sp.nb_bits = p.nb_bits; sp.dup = p.dup;
+  sp.nb_bits = p.nb_bits; sp.dup = p.dup; sp.qstream = p.qstream; sp.qtiles = p.qtiles;
   CUtensorMap tq, tdb;
   T2P_TRY(make_tmap_rows(&tq, d_q, B, D, sp.q_box_rows));
   T2P_TRY(make_tmap_rows(&tdb, d_db, N, D, sp.db_box_rows));
-  dim3 grid(p.G, p.qtiles);
+  dim3 grid(p.G, p.qstream ? 1 : p.qtiles);
   if (p.KP == 16) {
     T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
     retrieve_scan_tc_kernel<16><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, sp, part);

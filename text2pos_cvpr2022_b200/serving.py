@@ -21,6 +21,23 @@ from . import _lib
 from .modules import tokenize
 
 
+def _native_submit(lib, descriptions, B, st, graph, d_out, h_out, event, stream) -> Optional[bool]:
+    """One foreign call: stage + H2D + graph launch + D2H + event record on ``stream`` (``t2p_serving_submit``).
+    Returns True if the batch was launched, False if it has non-ASCII bytes (nothing enqueued)."""
+    if len(descriptions) != B:
+        raise ValueError(f"engine built for batches of {B} queries, got {len(descriptions)}")
+    blob = ("\0".join(descriptions) + "\0").encode("utf-8")
+    used, ascii_ = _lib._SZ(0), _lib._I(0)
+    rc = lib.t2p_serving_submit(blob, len(blob), B, st.h_stage_ptr, st.stage_cap, st.d_stage_ptr, graph.raw_cuda_graph_exec(),
+                                d_out.data_ptr(), h_out.data_ptr(), h_out.numel() * 8, event.cuda_event, stream.cuda_stream,
+                                _lib.C.byref(used), _lib.C.byref(ascii_))
+    if rc == -3:
+        raise ValueError("batch does not fit the staging buffer (raise max_text_bytes)")
+    _lib.check(rc, "serving_submit")
+    st.used_bytes = int(used.value)
+    return bool(ascii_.value)
+
+
 class _Slot:
     """One in-flight batch: staging buffers both ways, the text embedding, workspaces, a stream and its graphs."""
 
@@ -30,6 +47,7 @@ class _Slot:
         cap = eng.lib.t2p_stage_texts_capacity(B, B * eng.max_text_bytes)
         self.h_stage = torch.zeros(cap, dtype=torch.uint8).pin_memory()
         self.d_stage = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        self.h_stage_ptr, self.d_stage_ptr, self.stage_cap = self.h_stage.data_ptr(), self.d_stage.data_ptr(), int(cap)
         self.tokens = torch.zeros(B, T, dtype=torch.int32, device=dev)
         self.h_tokens = torch.zeros(B, T, dtype=torch.int32).pin_memory()
         self.h_lengths = torch.ones(B, dtype=torch.int32).pin_memory()
@@ -50,6 +68,7 @@ class _Slot:
             self.ws_lstm = torch.empty(max(256, eng.lib.t2p_lstm_encode_workspace(B, D)), dtype=torch.uint8, device=dev)
             self.stream = torch.cuda.Stream() if own_stream else None
             self.done = torch.cuda.Event()
+            self.done.record()  # creates the underlying cudaEvent_t (its raw handle goes to t2p_serving_submit)
         self.ws_topk = None
         self.graphs = {}
 
@@ -75,9 +94,10 @@ class OnlineRetrievalEngine:
         self.max_text_bytes = int(max_text_bytes)  # average bytes per description the staging buffer is sized for
         self.depth = max(1, int(depth))
         # LSTM clusters per direction: default 7 (lowest latency) for a synchronous engine; a pipelined one packs the batch
-        # into 2 clusters of two ping-pong groups each (half the SM-time per batch, so more batches share the chip)
+        # into 2 clusters (two ping-pong groups each) or, with >= 8 batches in flight, into 1 cluster of four groups:
+        # more latency per batch, a fraction of the SM-time, so more batches share the chip
         if lstm_clusters is None:
-            lstm_clusters = 2 if self.depth > 1 else 0
+            lstm_clusters = 0 if self.depth == 1 else (2 if self.depth < 8 else 1)
         if lstm_clusters:
             import copy
 
@@ -249,9 +269,11 @@ class OnlineRetrievalEngine:
             raise RuntimeError(f"{self.depth} batches already in flight: collect() first")
         slot = self._next
         s = self.slots[slot]
-        with torch.cuda.stream(s.stream):
-            self._enqueue_query(s, slot, descriptions, graph_key)
-            s.done.record()
+        g = s.graphs.get(graph_key) if graph_key is not None else None
+        if g is None or not _native_submit(self.lib, descriptions, self.B, s, g, s.d_out, s.h_out, s.done, s.stream):
+            with torch.cuda.stream(s.stream):  # no graph for this key, or a non-ASCII batch: the general path
+                self._enqueue_query(s, slot, descriptions, graph_key)
+                s.done.record()
         self._next = (self._next + 1) % self.depth
         self._inflight.append(slot)
         return slot
@@ -309,6 +331,7 @@ class _ShardSlot:
             n = e.lib.t2p_retrieve_topk_workspace(R * B, e.db.shape[0], e.db.shape[1], k)
             self.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=dev)
             self.done = torch.cuda.Event()
+            self.done.record()
         self.graphs = {}
 
 
@@ -487,9 +510,12 @@ class ShardedOnlineRetrievalEngine:
         if len(self._inflight) >= e.depth:
             raise RuntimeError(f"{e.depth} batches already in flight: collect() first")
         slot = self._next
-        with torch.cuda.stream(e.slots[slot].stream):
-            self._enqueue_query(slot, descriptions, graph_key)
-            self.slots[slot].done.record()
+        s, es = self.slots[slot], e.slots[slot]
+        g = s.graphs.get(graph_key) if graph_key is not None else None
+        if g is None or not _native_submit(e.lib, descriptions, e.B, es, g, s.d_final, s.h_final, s.done, es.stream):
+            with torch.cuda.stream(es.stream):
+                self._enqueue_query(slot, descriptions, graph_key)
+                s.done.record()
         self._next = (self._next + 1) % e.depth
         self._inflight.append(slot)
         return slot

@@ -252,6 +252,78 @@ def synth_queries(seed: int, n_queries: int, n_hints: int = NUM_HINTS) -> List[s
 
 
 # ----------------------------------------------------------------------------------------------
+# a KITTI360Pose-shaped coarse dataset (what training.coarse.eval_epoch / evaluation.pipeline.run_coarse consume)
+# ----------------------------------------------------------------------------------------------
+class SynthPose:
+    """Duck type of the reference ``Pose`` (imports.py:178-218): world position, its cell, six hint descriptions."""
+
+    def __init__(self, pose_w: np.ndarray, cell_id: str, hints: List[str]):
+        self.pose_w = pose_w
+        self.cell_id = cell_id
+        self.descriptions = hints
+
+
+class SynthCellDataset:
+    """``Kitti360CoarseCellOnlyDataset`` stand-in (dataloading/kitti360pose/cells.py:163-213)."""
+
+    def __init__(self, cells: List[SynthCell], seed: int):
+        self.cells = cells
+        self._points = {}
+        self._seed = seed
+
+    def __len__(self):
+        return len(self.cells)
+
+    def __getitem__(self, idx: int):
+        cell = self.cells[idx]
+        if idx not in self._points:  # FixedPoints resampling is random in the reference; seeded per cell here
+            self._points[idx] = batch_object_points(cell.objects, np.random.default_rng(self._seed + 7919 * idx))
+        return {"cells": cell, "cell_ids": cell.id, "objects": cell.objects, "object_points": self._points[idx]}
+
+
+class SynthCoarseDataset:
+    """``Kitti360CoarseDatasetMulti`` stand-in: ``n_poses`` poses spread over ``n_cells`` cells of one scene; the text of a
+    pose is its six template hints joined by a space (dataloading/kitti360pose/cells.py:82)."""
+
+    def __init__(self, seed: int, n_cells: int, n_poses: int):
+        rng = np.random.default_rng(seed)
+        self.all_cells = [synth_cell(rng, i) for i in range(n_cells)]
+        self.all_poses = []
+        for _ in range(n_poses):
+            c = self.all_cells[int(rng.integers(0, n_cells))]
+            pose_w = c.bbox_w[0:3] + rng.random(3) * c.cell_size
+            self.all_poses.append(SynthPose(pose_w, c.id, [synth_hint(rng) for _ in range(NUM_HINTS)]))
+        self._cell_dataset = SynthCellDataset(self.all_cells, seed)
+
+    def __len__(self):
+        return len(self.all_poses)
+
+    def __getitem__(self, idx: int):
+        pose = self.all_poses[idx]
+        return {"poses": pose, "texts": " ".join(pose.descriptions), "cell_ids": pose.cell_id}
+
+    def get_cell_dataset(self):
+        return self._cell_dataset
+
+
+class SynthLoader:
+    """``DataLoader(dataset, batch_size, collate_fn=dict-of-lists, shuffle=False)`` stand-in with the ``.dataset`` attribute
+    the reference's evaluation code reads."""
+
+    def __init__(self, dataset, batch_size: int):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+
+    def __iter__(self):
+        n = len(self.dataset)
+        for i0 in range(0, n, self.batch_size):
+            items = [self.dataset[i] for i in range(i0, min(i0 + self.batch_size, n))]
+            yield {k: [it[k] for it in items] for k in items[0]}
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+
+# ----------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------
 def synth_state_dict(spec: Sequence[Tuple[str, Sequence[int]]], seed: int, gain: float = 1.0) -> Dict[str, torch.Tensor]:

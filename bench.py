@@ -389,8 +389,9 @@ def main_b200(args):
                  "achieved": lstm_flops / (lstm_ms * 1e-3) / 1e12, "peak": peaks["bf16"], "unit": "TFLOP/s",
                  "traffic": NCU_TRAFFIC["lstm"], "ms": lstm_ms, "algorithmic_flops": lstm_flops,
                  "note": "~50 strictly dependent steps of a [64,256]x[256,1024] product per direction on tcgen05 (fp16 hi/lo split, "
-                         "3 products, fp32 accumulate; W_hh resident in tensor memory); latency-bound by the per-step h exchange over "
-                         "DSMEM, reported against the bf16 tensor peak"}
+                         "3 products, fp32 accumulate; W_hh resident in tensor memory); bound by the per-step h exchange over the "
+                         "SM-to-SM network, not by the tensor pipe: see roofline_network (the binding resource); reported here "
+                         "against the bf16 tensor peak as the contract asks"}
     roof_lstm["frac"] = roof_lstm["achieved"] / peaks["bf16"]
     # the resource that actually binds the recurrence: the SM-to-SM network.  Every CTA of a cluster sends
     # 7/8 of its 32-unit slice of h (fp16 hi + lo) of every sequence to its 7 peers and receives as much, every step.

@@ -145,6 +145,10 @@ typedef struct {
   t2p_linear_desc ga_l1, ga_l2; /* GlobalAbstraction mlp, k = 256 + 3 */
   t2p_linear_desc lin1, lin2;
   int32_t self_loop_quirk; /* PointConv(add_self_loops=True) flat-index self loops, see oracle/pointnet.py */
+  int32_t reserved;
+  int64_t sa_l2_tc_off[3]; /* per SA layer, or -1: fp16 hi/lo images of 2^8 * (BN-folded second layer) for the tensor-core
+                              kernel (csrc/sa_tc.cu), C1 = C2 = C in {128, 256}: [K chunk C/64][hi|lo][row n = output
+                              channel, C][64 fp16, k = 64*chunk + e, 16-byte units XOR-swizzled by (n & 7)] */
 } t2p_pointnet2_desc;
 
 size_t t2p_pointnet2_workspace(const t2p_pointnet2_desc* desc, int n_obj, int P);

@@ -209,3 +209,20 @@ def test_stage_texts_layout():
     assert not ascii2
     with pytest.raises(RuntimeError):
         vocab.stage_texts(["x" * 100], torch.zeros(32, dtype=torch.uint8))
+
+
+def test_sa_tensor_core_images_layout_and_split():
+    """packing._sa_tc_images: fp16 hi/lo split of 2^8*W2 in the 128-byte-swizzled K-major UMMA B layout, per 64-wide K chunk."""
+    rng = np.random.default_rng(2)
+    for C in (128, 256):
+        w = rng.uniform(-0.2, 0.2, size=(C, C))  # [K, N] as stored in the blob
+        img = packing._sa_tc_images(w).view(np.float16).reshape(C // 64, 2, C, 64)
+        for (k, n) in [(0, 0), (C - 1, C - 1), (70, 5), (63, 9), (64, 127)]:
+            chunk, lu, e = k // 64, (k % 64) // 8, k % 8
+            pu = lu ^ (n & 7)
+            v = w[k, n] * 256.0
+            hi, lo = float(img[chunk, 0, n, pu * 8 + e]), float(img[chunk, 1, n, pu * 8 + e])
+            assert hi == float(np.float16(v))
+            assert abs(hi + lo - v) <= 2.0 ** -21 * abs(v) + 1e-12
+        assert np.array_equal(np.sort(img[:, 0].astype(np.float64).reshape(-1)),
+                              np.sort((w * 256.0).astype(np.float16).astype(np.float64).reshape(-1)))

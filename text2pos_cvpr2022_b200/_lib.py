@@ -36,6 +36,8 @@ class PointNet2Desc(C.Structure):
         ("lin1", LinearDesc),
         ("lin2", LinearDesc),
         ("self_loop_quirk", C.c_int32),
+        ("reserved", C.c_int32),
+        ("sa_l2_tc_off", C.c_int64 * 3),
     ]
 
 

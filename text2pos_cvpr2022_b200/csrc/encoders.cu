@@ -59,6 +59,19 @@ static size_t pn_carve(const PnDims& d, int n_obj, Arena& a, PnWorkspace* w) {
 
 }  // namespace
 
+namespace {
+int sm_count_cached() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sms = prop.multiProcessorCount;
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+}  // namespace
+
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------------
@@ -138,8 +151,15 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
                                  ws.T, C1, s));
     T2P_TRY(launch_linear(ws.cpos[l], n_obj * m, 3, 3, W1 + (size_t)Cin * C1, nullptr, C1, false, ws.S, C1, s));
     T2P_CUDA(cudaMemsetAsync(ws.x[l], 0, (size_t)n_obj * m * C2 * sizeof(float), s));
-    T2P_TRY(launch_sa_edge(ws.T, ws.S, ws.nbr, ws.cnt, d_obj_cell_start, desc->self_loop_quirk, n_obj, Pd, m, C1,
-                           wptr(w, desc->sa_l2[l].w_off), wptr(w, desc->sa_l2[l].b_off), C2, ws.x[l], s));
+    if (desc->sa_l2_tc_off[l] >= 0 && sa_edge_tc_supported(C1, C2, m) &&
+        (size_t)desc->sa_l2_tc_off[l] + (size_t)C1 * C2 <= w->n_floats) {
+      // second layer + ReLU + max on the tensor cores (fp16 hi/lo split, fp32 accumulate)
+      T2P_TRY(launch_sa_edge_tc(ws.T, ws.S, ws.nbr, ws.cnt, d_obj_cell_start, desc->self_loop_quirk, n_obj, Pd, m, C1,
+                                wptr(w, desc->sa_l2_tc_off[l]), wptr(w, desc->sa_l2[l].b_off), ws.x[l], sm_count_cached(), s));
+    } else {
+      T2P_TRY(launch_sa_edge(ws.T, ws.S, ws.nbr, ws.cnt, d_obj_cell_start, desc->self_loop_quirk, n_obj, Pd, m, C1,
+                             wptr(w, desc->sa_l2[l].w_off), wptr(w, desc->sa_l2[l].b_off), C2, ws.x[l], s));
+    }
     if (d_dbg_idx && d_dbg_idx[l])
       T2P_CUDA(cudaMemcpyAsync(d_dbg_idx[l], ws.ctr_idx, (size_t)n_obj * m * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     if (d_dbg_nbr && d_dbg_nbr[l])

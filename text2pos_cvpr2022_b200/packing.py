@@ -94,7 +94,35 @@ def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = Tru
     d.lin1 = bb.linear(_np64(sd[prefix + "lin1.weight"]), _np64(sd[prefix + "lin1.bias"]))
     d.lin2 = bb.linear(_np64(sd[prefix + "lin2.weight"]), _np64(sd[prefix + "lin2.bias"]))
     d.self_loop_quirk = 1 if self_loop_quirk else 0
+    for l in range(3):
+        k, n = d.sa_l2[l].k, d.sa_l2[l].n
+        if k == n and k in (128, 256):
+            blob_w = np.concatenate(bb.chunks)[d.sa_l2[l].w_off: d.sa_l2[l].w_off + k * n].astype(np.float64).reshape(k, n)
+            d.sa_l2_tc_off[l] = bb.add_raw_u32(_sa_tc_images(blob_w))
+        else:
+            d.sa_l2_tc_off[l] = -1
     return d
+
+
+SA_TC_WSCALE = 256.0  # 2^8: keeps the fp16 "lo" halves of the weights out of the subnormal range
+
+
+def _sa_tc_images(w_kn: np.ndarray) -> np.ndarray:
+    """w_kn [C, C] (= the BN-folded second local_nn layer as stored in the blob, [K, N]) -> uint32 words of the UMMA B-operand
+    images streamed by ``sa_edge_tc_kernel``: [K chunk C/64][hi|lo][row n (output channel) C][64 fp16], value = fp16 split of
+    2^8 * W[k = 64*chunk + e][n], the eight 16-byte units of every 128-byte row stored at (unit XOR (n & 7))."""
+    C = w_kn.shape[0]
+    assert w_kn.shape == (C, C) and C % 64 == 0
+    w = w_kn.T * SA_TC_WSCALE                      # [n, k]
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float64)).astype(np.float16)
+    n = np.arange(C)
+    swz = np.arange(8)[None, :] ^ (n[:, None] & 7)  # physical unit v of row n holds logical unit v ^ (n & 7)
+    out = np.zeros((C // 64, 2, C, 8, 8), dtype=np.float16)
+    for part, mat in enumerate((hi, lo)):
+        t = mat.reshape(C, C // 64, 8, 8).transpose(1, 0, 2, 3)  # [chunk, n, logical unit, elem]
+        out[:, part] = np.take_along_axis(t, swz[None, :, :, None], axis=2)
+    return out.reshape(-1).view(np.uint32)
 
 
 def pack_object_encoder(bb: BlobBuilder, sd, prefix: str, embed_dim: int) -> _lib.ObjEncDesc:

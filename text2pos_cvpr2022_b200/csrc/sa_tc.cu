@@ -247,15 +247,26 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
             for (uint32_t off = 0; off < 2u * W_PART; off += 16384u) sat_bulk_load(dst + off, src + off, 16384u, &bars->full[stage]);
           }
           const int col0 = kc * 64 + cg * 8;
-#pragma unroll 2
+          // all 16 T loads of this lane (8 rows x 32 bytes) are issued before the first use: one L2 round trip per chunk
+          // instead of one per row; the S rows repeat from row to row (a centre has up to 33 edges) and hit L1
+          float4 tv[8][2];
+          int rsv[8];
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = pw * 32 + i * 4 + rsub;
-            const int rs = rw->rowS[r];
+            rsv[i] = rw->rowS[r];
+            const float4* tp = reinterpret_cast<const float4*>(T + (size_t)rw->rowT[r] * C + col0);
+            tv[i][0] = rsv[i] >= 0 ? __ldg(tp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tv[i][1] = rsv[i] >= 0 ? __ldg(tp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = pw * 32 + i * 4 + rsub;
+            const int rs = rsv[i];
             uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
             if (rs >= 0) {
-              const float4* tp = reinterpret_cast<const float4*>(T + (size_t)rw->rowT[r] * C + col0);
               const float4* sp = reinterpret_cast<const float4*>(S + (size_t)rs * C + col0);
-              const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+              const float4 t0 = tv[i][0], t1 = tv[i][1], s0 = __ldg(sp), s1 = __ldg(sp + 1);
               const float a[8] = {fmaxf(t0.x - s0.x, 0.f), fmaxf(t0.y - s0.y, 0.f), fmaxf(t0.z - s0.z, 0.f), fmaxf(t0.w - s0.w, 0.f),
                                   fmaxf(t1.x - s1.x, 0.f), fmaxf(t1.y - s1.y, 0.f), fmaxf(t1.z - s1.z, 0.f), fmaxf(t1.w - s1.w, 0.f)};
               uint32_t h[4], l[4];

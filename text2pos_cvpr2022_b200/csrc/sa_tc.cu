@@ -3,7 +3,8 @@
 //
 //   out[o, c, :] = max over the edges (j -> c) of object o of  relu( relu(T_j - S_c) . W2 + b2 )
 //
-// Persistent CTAs, one work item = 128 consecutive edges of one object (edges packed centre by centre; the packing, the
+// Persistent CTAs (objects dealt round-robin), one work item = 128 consecutive edges of one object (edges packed centre by
+// centre; the packing, the
 // self-loop quirk and the gather indices are those of the fp32 kernel sa_edge_kernel, csrc/dense.cu).  Ten warps:
 //   warp 0      builds the row table of the NEXT item (prefix sum of the per-centre edge counts, one binary search per
 //               row, neighbour lookup) while the current one is processed;
@@ -78,7 +79,7 @@ template <int C>
 __global__ void __launch_bounds__(SAT_THREADS, 1)
 sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, const int32_t* __restrict__ nbr,
                   const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int P, int m,
-                  int n_obj, int tiles_per_obj, const uint4* __restrict__ w_img, const float* __restrict__ b2,
+                  int n_obj, const uint4* __restrict__ w_img, const float* __restrict__ b2,
                   float* __restrict__ out) {
   constexpr int NKC = C / 64;                    // 64-wide K chunks
   constexpr int A_PART = SAT_ROWS * 128;         // one of {hi, lo} of an A chunk: 128 rows x 128 bytes
@@ -95,8 +96,6 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
   SatBars* bars = reinterpret_cast<SatBars*>(rows + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_items = n_obj * tiles_per_obj;
-  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
     for (int s = 0; s < SAT_STAGES; ++s) {
@@ -118,18 +117,26 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
   const uint32_t tmem_base = bars->tmem_slot;
 
   if (warp == 0) {
-    // ===== row tables, one item ahead =====
-    for (int it = 0; it < my_items; ++it) {
-      const int item = (int)blockIdx.x + it * (int)gridDim.x;
-      const int o = item / tiles_per_obj, t = item - o * tiles_per_obj;
-      const int buf = it & 1;
-      mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-      SatRows* rw = rows + buf;
+    // ===== row tables, one item ahead.  Objects are dealt round-robin to the CTAs; the per-centre edge counts of an object
+    // are read once (the next object's are prefetched), its tiles are exactly ceil(E/128); a final table with
+    // n_valid = -1 tells the consumers to stop. =====
+    const int extra = quirk ? 1 : 0;
+    const int c0 = 2 * lane, c1 = 2 * lane + 1;
+    int it = 0;
+    int o = (int)blockIdx.x;
+    int n0 = 0, n1 = 0;
+    if (o < n_obj) {
+      n0 = c0 < m ? __ldg(cnt + (size_t)o * m + c0) + extra : 0;
+      n1 = c1 < m ? __ldg(cnt + (size_t)o * m + c1) + extra : 0;
+    }
+    for (; o < n_obj; o += (int)gridDim.x) {
+      const int o_next = o + (int)gridDim.x;
+      int p0 = 0, p1 = 0;  // prefetch of the next object's counts
+      if (o_next < n_obj) {
+        p0 = c0 < m ? __ldg(cnt + (size_t)o_next * m + c0) + extra : 0;
+        p1 = c1 < m ? __ldg(cnt + (size_t)o_next * m + c1) + extra : 0;
+      }
       // inclusive prefix of the per-centre edge counts (m <= 64: two entries per lane)
-      const int extra = quirk ? 1 : 0;
-      const int c0 = 2 * lane, c1 = 2 * lane + 1;
-      const int n0 = c0 < m ? __ldg(cnt + (size_t)o * m + c0) + extra : 0;
-      const int n1 = c1 < m ? __ldg(cnt + (size_t)o * m + c1) + extra : 0;
       int inc = n0 + n1;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -138,52 +145,59 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       }
       const int E = __shfl_sync(0xffffffffu, inc, 31);
       const int incl1 = inc, incl0 = inc - n1;  // inclusive prefix at c1, c0
-      const int e_base = t * SAT_ROWS;
-      int n_valid = 0;
-      if (e_base < E) {
-        n_valid = min(SAT_ROWS, E - e_base);
+      const int first = quirk ? __ldg(obj_cell_start + o) : 0;
+      for (int e_base = 0; e_base < E; e_base += SAT_ROWS, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        SatRows* rw = rows + buf;
 #pragma unroll
         for (int rr = 0; rr < SAT_ROWS / 32; ++rr) {
           const int r = rr * 32 + lane;
           const int e = e_base + r;
           int rt = 0, rs = -1;
-          {
-            // smallest centre c with incl[c] > e: binary search over the 2m prefix values held two per lane.  Every lane
-            // runs the same 6 rounds (m <= 64) -- the shuffles sit in convergent code -- and out-of-range rows are masked after.
-            const int ee = min(e, E - 1);
-            int lo = 0, hi = m - 1;
+          // smallest centre c with incl[c] > e: binary search over the 2m prefix values held two per lane.  Every lane
+          // runs the same 6 rounds (m <= 64) -- the shuffles sit in convergent code -- and out-of-range rows are masked after.
+          const int ee = min(e, E - 1);
+          int lo = 0, hi = m - 1;
 #pragma unroll
-            for (int round = 0; round < 6; ++round) {
-              const int mid = (lo + hi) >> 1;
-              const int pv1 = __shfl_sync(0xffffffffu, incl1, mid >> 1), pv0 = __shfl_sync(0xffffffffu, incl0, mid >> 1);
-              const int pv = (mid & 1) ? pv1 : pv0;
-              if (lo < hi) {
-                if (pv > ee) hi = mid; else lo = mid + 1;
-              }
+          for (int round = 0; round < 6; ++round) {
+            const int mid = (lo + hi) >> 1;
+            const int pv1 = __shfl_sync(0xffffffffu, incl1, mid >> 1), pv0 = __shfl_sync(0xffffffffu, incl0, mid >> 1);
+            const int pv = (mid & 1) ? pv1 : pv0;
+            if (lo < hi) {
+              if (pv > ee) hi = mid; else lo = mid + 1;
             }
-            const int c = lo;
-            const int q1 = __shfl_sync(0xffffffffu, incl1, c >> 1), q0 = __shfl_sync(0xffffffffu, incl0, c >> 1);
-            const int nn1 = __shfl_sync(0xffffffffu, n1, c >> 1), nn0 = __shfl_sync(0xffffffffu, n0, c >> 1);
-            if (e < E) {
-              const int incl_c = (c & 1) ? q1 : q0;
-              const int n_c = (c & 1) ? nn1 : nn0;
-              const int slot = e - (incl_c - n_c);
-              const int cn = n_c - extra;
-              if (slot < cn) {
-                rt = o * P + __ldg(nbr + ((size_t)o * m + c) * T2P_MAX_NEIGHBORS + slot);
-              } else {  // flat-index self loop (see sa_edge_kernel)
-                const int first = __ldg(obj_cell_start + o);
-                const int flat = (o - first) * m + c;
-                rt = (first + flat / P) * P + flat % P;
-              }
-              rs = o * m + c;
+          }
+          const int c = lo;
+          const int q1 = __shfl_sync(0xffffffffu, incl1, c >> 1), q0 = __shfl_sync(0xffffffffu, incl0, c >> 1);
+          const int nn1 = __shfl_sync(0xffffffffu, n1, c >> 1), nn0 = __shfl_sync(0xffffffffu, n0, c >> 1);
+          if (e < E) {
+            const int incl_c = (c & 1) ? q1 : q0;
+            const int n_c = (c & 1) ? nn1 : nn0;
+            const int slot = e - (incl_c - n_c);
+            const int cn = n_c - extra;
+            if (slot < cn) {
+              rt = o * P + __ldg(nbr + ((size_t)o * m + c) * T2P_MAX_NEIGHBORS + slot);
+            } else {  // flat-index self loop (see sa_edge_kernel)
+              const int flat = (o - first) * m + c;
+              rt = (first + flat / P) * P + flat % P;
             }
+            rs = o * m + c;
           }
           rw->rowT[r] = rt;
           rw->rowS[r] = rs;
         }
+        if (lane == 0) rw->n_valid = min(SAT_ROWS, E - e_base);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->rows_full[buf]);
       }
-      if (lane == 0) rw->n_valid = n_valid;
+      n0 = p0;
+      n1 = p1;
+    }
+    {  // terminator
+      const int buf = it & 1;
+      mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+      if (lane == 0) rows[buf].n_valid = -1;
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_full[buf]);
     }
@@ -193,10 +207,11 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     const uint32_t st_addr = smem_u32(stages);
     int stage = 0, nv = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < my_items; ++it) {
+    for (int it = 0;; ++it) {
       const int buf = it & 1;
       mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
       const int n_valid = rows[buf].n_valid;
+      if (n_valid < 0) break;
       if (n_valid > 0) {
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_empty[acc], (uint32_t)(((nv >> 1) & 1) ^ 1));
@@ -232,10 +247,11 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     const int cg = lane & 7, rsub = lane >> 3;
     int stage = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < my_items; ++it) {
+    for (int it = 0;; ++it) {
       const int buf = it & 1;
       mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
       const SatRows* rw = rows + buf;
+      if (rw->n_valid < 0) break;
       if (rw->n_valid > 0) {
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait(&bars->empty[stage], ph ^ 1);
@@ -301,10 +317,11 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     const int et = (warp - 6) * 32 + lane;     // 0..127: thread index inside the epilogue group
     const int ccol = et & 31, rgrp = et >> 5;  // column pass: column of the 32-chunk, group of 32 rows
     int nv = 0;
-    for (int it = 0; it < my_items; ++it) {
+    for (int it = 0;; ++it) {
       const int buf = it & 1;
       mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
       const SatRows* rw = rows + buf;
+      if (rw->n_valid < 0) break;
       if (rw->n_valid > 0) {
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_full[acc], (uint32_t)((nv >> 1) & 1));
@@ -363,11 +380,8 @@ static int launch_sa_tc(const float* T, const float* S, const int32_t* nbr, cons
   const size_t smem = sat_smem_bytes<C>();
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "set abstraction (tensor cores): %zu bytes of shared memory", smem);
   T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int rows_max = m * (T2P_MAX_NEIGHBORS + (quirk ? 1 : 0));
-  const int tiles_per_obj = (rows_max + SAT_ROWS - 1) / SAT_ROWS;
-  const long long items = (long long)n_obj * tiles_per_obj;
-  const int grid = (int)std::min<long long>(items, sms);
-  sa_edge_tc_kernel<C><<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj, tiles_per_obj,
+  const int grid = std::min(n_obj, sms);  // objects are dealt round-robin to persistent CTAs
+  sa_edge_tc_kernel<C><<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj,
                                                       reinterpret_cast<const uint4*>(w_img), b2, out);
   T2P_LAUNCH_CHECK();
   return T2P_OK;

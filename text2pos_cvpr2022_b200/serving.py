@@ -21,21 +21,26 @@ from . import _lib
 from .modules import tokenize
 
 
-def _native_submit(lib, descriptions, B, st, graph, d_out, h_out, event, stream) -> Optional[bool]:
+def _native_submit(lib, descriptions, B, st, key, graph, d_out, h_out, event, stream) -> Optional[bool]:
     """One foreign call: stage + H2D + graph launch + D2H + event record on ``stream`` (``t2p_serving_submit``).
-    Returns True if the batch was launched, False if it has non-ASCII bytes (nothing enqueued)."""
+    Returns True if the batch was launched, False if it has non-ASCII bytes (nothing enqueued).  The raw handles of
+    (slot, graph) are looked up once and cached: the per-batch host work is one join/encode and one ctypes call."""
     if len(descriptions) != B:
         raise ValueError(f"engine built for batches of {B} queries, got {len(descriptions)}")
+    raw = st.raw.get(key)
+    if raw is None:
+        raw = st.raw[key] = (graph.raw_cuda_graph_exec(), d_out.data_ptr(), h_out.data_ptr(), h_out.numel() * 8,
+                             event.cuda_event, stream.cuda_stream)
     blob = ("\0".join(descriptions) + "\0").encode("utf-8")
-    used, ascii_ = _lib._SZ(0), _lib._I(0)
-    rc = lib.t2p_serving_submit(blob, len(blob), B, st.h_stage_ptr, st.stage_cap, st.d_stage_ptr, graph.raw_cuda_graph_exec(),
-                                d_out.data_ptr(), h_out.data_ptr(), h_out.numel() * 8, event.cuda_event, stream.cuda_stream,
-                                _lib.C.byref(used), _lib.C.byref(ascii_))
+    used, ascii_ = st.c_used, st.c_ascii
+    rc = lib.t2p_serving_submit(blob, len(blob), B, st.h_stage_ptr, st.stage_cap, st.d_stage_ptr, raw[0], raw[1], raw[2], raw[3],
+                                raw[4], raw[5], st.c_used_ref, st.c_ascii_ref)
     if rc == -3:
         raise ValueError("batch does not fit the staging buffer (raise max_text_bytes)")
-    _lib.check(rc, "serving_submit")
-    st.used_bytes = int(used.value)
-    return bool(ascii_.value)
+    if rc != 0:
+        _lib.check(rc, "serving_submit")
+    st.used_bytes = used.value
+    return ascii_.value != 0
 
 
 class _Slot:
@@ -48,6 +53,9 @@ class _Slot:
         self.h_stage = torch.zeros(cap, dtype=torch.uint8).pin_memory()
         self.d_stage = torch.zeros(cap, dtype=torch.uint8, device=dev)
         self.h_stage_ptr, self.d_stage_ptr, self.stage_cap = self.h_stage.data_ptr(), self.d_stage.data_ptr(), int(cap)
+        self.raw = {}  # graph key -> raw handles for t2p_serving_submit
+        self.c_used, self.c_ascii = _lib._SZ(0), _lib._I(0)
+        self.c_used_ref, self.c_ascii_ref = _lib.C.byref(self.c_used), _lib.C.byref(self.c_ascii)
         self.tokens = torch.zeros(B, T, dtype=torch.int32, device=dev)
         self.h_tokens = torch.zeros(B, T, dtype=torch.int32).pin_memory()
         self.h_lengths = torch.ones(B, dtype=torch.int32).pin_memory()
@@ -62,6 +70,7 @@ class _Slot:
         self.h_scores = self.h_out[: B * k].view(torch.float64).view(B, k)
         self.h_idx = self.h_out[B * k: 2 * B * k].view(B, k)
         self.h_counts = self.h_out[2 * B * k:].view(torch.int32)[:B].numpy()
+        self.np_idx, self.np_scores = self.h_idx.numpy(), self.h_scores.numpy()  # views of the pinned result buffer
         self.used_bytes = 0
         self.q = torch.empty(B, D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -130,6 +139,7 @@ class OnlineRetrievalEngine:
             for s in self.slots:
                 s.ws_topk = torch.empty(max(256, n), dtype=torch.uint8, device=self.device)
                 s.graphs = {}
+                s.raw = {}
 
     # ---- one step on the current stream ---------------------------------------------------------------------------
     def enqueue_encode(self, tokens: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None, slot: int = 0):
@@ -179,6 +189,7 @@ class OnlineRetrievalEngine:
             with torch.cuda.graph(g):
                 self.enqueue_step(db, slot=slot)
             self.slots[slot].graphs[key] = g
+            self.slots[slot].raw.pop(key, None)
         return g
 
     def capture_all(self, key=0, db: Optional[torch.Tensor] = None):
@@ -270,7 +281,7 @@ class OnlineRetrievalEngine:
         slot = self._next
         s = self.slots[slot]
         g = s.graphs.get(graph_key) if graph_key is not None else None
-        if g is None or not _native_submit(self.lib, descriptions, self.B, s, g, s.d_out, s.h_out, s.done, s.stream):
+        if g is None or not _native_submit(self.lib, descriptions, self.B, s, graph_key, g, s.d_out, s.h_out, s.done, s.stream):
             with torch.cuda.stream(s.stream):  # no graph for this key, or a non-ASCII batch: the general path
                 self._enqueue_query(s, slot, descriptions, graph_key)
                 s.done.record()
@@ -285,7 +296,7 @@ class OnlineRetrievalEngine:
         s = self.slots[slot]
         s.done.synchronize()
         self._check_counts(s)
-        return s.h_idx.numpy(), s.h_scores.numpy()
+        return s.np_idx, s.np_scores
 
     def h2d_bytes(self) -> int:
         """Bytes of the last staged batch of slot 0 (raw text + offsets; they vary with the text)."""
@@ -465,6 +476,7 @@ class ShardedOnlineRetrievalEngine:
                 self.enqueue_step(db, slot=slot)
                 self.slots[slot].final_counts.copy_(e.slots[slot].lengths)
             self.slots[slot].graphs[key] = g
+            e.slots[slot].raw.pop(("sharded", key), None)
         return g
 
     def capture_all(self, key=0, db: Optional[torch.Tensor] = None):
@@ -512,7 +524,7 @@ class ShardedOnlineRetrievalEngine:
         slot = self._next
         s, es = self.slots[slot], e.slots[slot]
         g = s.graphs.get(graph_key) if graph_key is not None else None
-        if g is None or not _native_submit(e.lib, descriptions, e.B, es, g, s.d_final, s.h_final, s.done, es.stream):
+        if g is None or not _native_submit(e.lib, descriptions, e.B, es, ("sharded", graph_key), g, s.d_final, s.h_final, s.done, es.stream):
             with torch.cuda.stream(es.stream):
                 self._enqueue_query(slot, descriptions, graph_key)
                 s.done.record()

@@ -146,6 +146,8 @@ typedef struct {
   t2p_linear_desc lin1, lin2;
   int32_t self_loop_quirk; /* PointConv(add_self_loops=True) flat-index self loops, see oracle/pointnet.py */
   int32_t reserved;
+  int64_t ga_l2_tc_off;    /* or -1: the same images for the second global-abstraction layer (K = 512, N = 1024), one set per
+                              256-wide column block: [N/256][K chunk 8][hi|lo][row n 256][64 fp16 swizzled] */
   int64_t sa_l2_tc_off[3]; /* per SA layer, or -1: fp16 hi/lo images of 2^8 * (BN-folded second layer) for the tensor-core
                               kernel (csrc/sa_tc.cu), C1 = C2 = C in {128, 256}: [K chunk C/64][hi|lo][row n = output
                               channel, C][64 fp16, k = 64*chunk + e, 16-byte units XOR-swizzled by (n & 7)] */

@@ -154,16 +154,18 @@ def test_set_abstraction_tensor_core_equals_fp32_kernel(coarse_model):
     cells = syn.synth_packed_cells(12, 40).to("cuda")  # ~450 objects: several waves of work items per CTA
     start = obj_cell_start_from_offsets(cells.cell_offsets)
     _, desc = pn.t2p_packed()
-    assert desc.sa_l2_tc_off[1] >= 0 and desc.sa_l2_tc_off[2] >= 0 and desc.sa_l2_tc_off[0] < 0
+    assert desc.sa_l2_tc_off[1] >= 0 and desc.sa_l2_tc_off[2] >= 0 and desc.sa_l2_tc_off[0] < 0 and desc.ga_l2_tc_off >= 0
     f_tc, dbg_tc = pn.features_packed(cells.pos, cells.rgb, start, debug=True)
-    saved = [desc.sa_l2_tc_off[i] for i in range(3)]
-    try:
+    saved = [desc.sa_l2_tc_off[i] for i in range(3)], desc.ga_l2_tc_off
+    try:  # the same forward with every tensor-core layer (SA2, SA3, second global-abstraction layer) on the fp32 kernels
         for i in range(3):
             desc.sa_l2_tc_off[i] = -1
+        desc.ga_l2_tc_off = -1
         f_32, dbg_32 = pn.features_packed(cells.pos, cells.rgb, start, debug=True)
     finally:
         for i in range(3):
-            desc.sa_l2_tc_off[i] = saved[i]
+            desc.sa_l2_tc_off[i] = saved[0][i]
+        desc.ga_l2_tc_off = saved[1]
     for l in (1, 2):
         a, b = dbg_tc["x"][l].cpu().numpy(), dbg_32["x"][l].cpu().numpy()
         np.testing.assert_allclose(a, b, atol=1e-5 * max(1.0, float(np.abs(b).max())), rtol=1e-5)

@@ -37,6 +37,7 @@ class PointNet2Desc(C.Structure):
         ("lin2", LinearDesc),
         ("self_loop_quirk", C.c_int32),
         ("reserved", C.c_int32),
+        ("ga_l2_tc_off", C.c_int64),
         ("sa_l2_tc_off", C.c_int64 * 3),
     ]
 

@@ -177,8 +177,14 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
   T2P_TRY(launch_linear_concat(x_in, d.C2[2], d.C2[2], pos_in, 3, 3, n_obj * m3, wptr(w, desc->ga_l1.w_off),
                                wptr(w, desc->ga_l1.b_off), d.ga_h, true, ws.gah, d.ga_h, s));
   T2P_CUDA(cudaMemsetAsync(ws.f0, 0, (size_t)n_obj * d.ga_o * sizeof(float), s));
-  T2P_TRY(launch_linear_groupmax(ws.gah, d.ga_h, d.ga_h, nullptr, 0, 0, n_obj * m3, wptr(w, desc->ga_l2.w_off),
-                                 wptr(w, desc->ga_l2.b_off), d.ga_o, m3, ws.f0, d.ga_o, s));
+  if (desc->ga_l2_tc_off >= 0 && linear_groupmax_tc_supported(d.ga_h, d.ga_o) &&
+      (size_t)desc->ga_l2_tc_off + (size_t)d.ga_h * d.ga_o <= w->n_floats) {
+    T2P_TRY(launch_linear_groupmax_tc(ws.gah, n_obj * m3, d.ga_h, wptr(w, desc->ga_l2_tc_off), wptr(w, desc->ga_l2.b_off), d.ga_o,
+                                      m3, ws.f0, sm_count_cached(), s));
+  } else {
+    T2P_TRY(launch_linear_groupmax(ws.gah, d.ga_h, d.ga_h, nullptr, 0, 0, n_obj * m3, wptr(w, desc->ga_l2.w_off),
+                                   wptr(w, desc->ga_l2.b_off), d.ga_o, m3, ws.f0, d.ga_o, s));
+  }
   T2P_TRY(launch_linear(ws.f0, n_obj, d.ga_o, d.ga_o, wptr(w, desc->lin1.w_off), wptr(w, desc->lin1.b_off), d.f1, true,
                         ws.f1, d.f1, s));
   T2P_TRY(launch_linear(ws.f1, n_obj, d.f1, d.f1, wptr(w, desc->lin2.w_off), wptr(w, desc->lin2.b_off), d.f2, true,

@@ -33,6 +33,9 @@ bool sa_edge_tc_supported(int C1, int C2, int m);
 int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt, const int32_t* obj_cell_start,
                       int quirk, int n_obj, int P, int m, int C, const float* w_img, const float* b2, float* out, int sms,
                       cudaStream_t s);
+bool linear_groupmax_tc_supported(int K, int N);
+int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, const float* bias, int N, int group, float* out,
+                              int sms, cudaStream_t s);
 int launch_fps_ball(const float* pos, int n_obj, int P, int m, float r2, int32_t* ctr_idx, float* cpos,
                     int32_t* nbr, int32_t* cnt, cudaStream_t s);
 int launch_fps_ball_mode(const float* pos, int n_obj, int P, int m, float r2, int mode, int do_ball, int32_t* ctr_idx,

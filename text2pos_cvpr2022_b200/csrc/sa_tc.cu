@@ -75,17 +75,25 @@ __host__ __device__ constexpr uint32_t sat_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // fp16 x fp16 -> fp32, both K-major
 }
 
-template <int C>
+// K = input channels, N = output channels of this launch's column block (blockIdx.y selects it), DENSE = false: set
+// abstraction (gathered edges, K == N == C); DENSE = true: a plain linear layer + ReLU + max over groups of `m` consecutive
+// rows (the global abstraction layer of PointNet++, models/pointcloud/pointnet2.py:45-49): rows = n_obj, T = the input.
+template <int K, int N, bool DENSE>
 __global__ void __launch_bounds__(SAT_THREADS, 1)
 sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, const int32_t* __restrict__ nbr,
                   const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int P, int m,
                   int n_obj, const uint4* __restrict__ w_img, const float* __restrict__ b2,
-                  float* __restrict__ out) {
-  constexpr int NKC = C / 64;                    // 64-wide K chunks
+                  float* __restrict__ out, int ldo) {
+  constexpr int C = K;                           // row pitch of T / S
+  constexpr int NKC = K / 64;                    // 64-wide K chunks
   constexpr int A_PART = SAT_ROWS * 128;         // one of {hi, lo} of an A chunk: 128 rows x 128 bytes
-  constexpr int W_PART = C * 128;                // one of {hi, lo} of a W chunk: C rows x 128 bytes
+  constexpr int W_PART = N * 128;                // one of {hi, lo} of a W chunk: N rows x 128 bytes
   constexpr int STAGE_BYTES = 2 * A_PART + 2 * W_PART;
-  constexpr int TMEM_COLS = 2 * C;               // two accumulators
+  constexpr int TMEM_COLS = 2 * N;               // two accumulators
+  const int n_off = (int)blockIdx.y * N;         // first output column of this CTA
+  w_img += (size_t)blockIdx.y * (NKC * 2 * W_PART / 16);
+  b2 += n_off;
+  out += n_off;
   constexpr int EPI_PITCH = 33;                  // floats per row of the transpose buffer (32 columns + 1: conflict-free)
 
   extern __shared__ __align__(1024) uint8_t sat_raw[];
@@ -120,10 +128,26 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     // ===== row tables, one item ahead.  Objects are dealt round-robin to the CTAs; the per-centre edge counts of an object
     // are read once (the next object's are prefetched), its tiles are exactly ceil(E/128); a final table with
     // n_valid = -1 tells the consumers to stop. =====
+    int it = 0;
+    if (DENSE) {  // rows [128 tile, +128) of the n_obj input rows; output row = input row / m
+      for (int tile = (int)blockIdx.x; tile * SAT_ROWS < n_obj; tile += (int)gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        SatRows* rw = rows + buf;
+#pragma unroll
+        for (int rr = 0; rr < SAT_ROWS / 32; ++rr) {
+          const int r = rr * 32 + lane, e = tile * SAT_ROWS + r;
+          rw->rowT[r] = e < n_obj ? e : 0;
+          rw->rowS[r] = e < n_obj ? e / m : -1;
+        }
+        if (lane == 0) rw->n_valid = min(SAT_ROWS, n_obj - tile * SAT_ROWS);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->rows_full[buf]);
+      }
+    }
     const int extra = quirk ? 1 : 0;
     const int c0 = 2 * lane, c1 = 2 * lane + 1;
-    int it = 0;
-    int o = (int)blockIdx.x;
+    int o = DENSE ? n_obj : (int)blockIdx.x;
     int n0 = 0, n1 = 0;
     if (o < n_obj) {
       n0 = c0 < m ? __ldg(cnt + (size_t)o * m + c0) + extra : 0;
@@ -203,7 +227,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     }
   } else if (warp == 1) {
     // ===== UMMA issuer =====
-    const uint32_t idesc = sat_idesc(SAT_ROWS, C);
+    const uint32_t idesc = sat_idesc(SAT_ROWS, N);
     const uint32_t st_addr = smem_u32(stages);
     int stage = 0, nv = 0;
     uint32_t ph = 0;
@@ -216,7 +240,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_empty[acc], (uint32_t)(((nv >> 1) & 1) ^ 1));
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * C;
+        const uint32_t d_tmem = tmem_base + acc * N;
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait(&bars->full[stage], ph);
           tc_fence_after_sync();
@@ -281,8 +305,13 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
             const int rs = rsv[i];
             uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
             if (rs >= 0) {
-              const float4* sp = reinterpret_cast<const float4*>(S + (size_t)rs * C + col0);
-              const float4 t0 = tv[i][0], t1 = tv[i][1], s0 = __ldg(sp), s1 = __ldg(sp + 1);
+              float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+              if (!DENSE) {
+                const float4* sp = reinterpret_cast<const float4*>(S + (size_t)rs * C + col0);
+                s0 = __ldg(sp);
+                s1 = __ldg(sp + 1);
+              }
+              const float4 t0 = tv[i][0], t1 = tv[i][1];
               const float a[8] = {fmaxf(t0.x - s0.x, 0.f), fmaxf(t0.y - s0.y, 0.f), fmaxf(t0.z - s0.z, 0.f), fmaxf(t0.w - s0.w, 0.f),
                                   fmaxf(t1.x - s1.x, 0.f), fmaxf(t1.y - s1.y, 0.f), fmaxf(t1.z - s1.z, 0.f), fmaxf(t1.w - s1.w, 0.f)};
               uint32_t h[4], l[4];
@@ -326,9 +355,9 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_full[acc], (uint32_t)((nv >> 1) & 1));
         tc_fence_after_sync();
-        for (int cc = 0; cc < C / 32; ++cc) {
+        for (int cc = 0; cc < N / 32; ++cc) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * C + cc * 32, v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * N + cc * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -342,13 +371,13 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
             for (int r = r0; r < r0 + 32; ++r) {
               const int rs = rw->rowS[r];
               if (rs != cur) {
-                if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * C + cc * 32 + ccol, best);
+                if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + cc * 32 + ccol, best);
                 cur = rs;
                 best = 0.f;
               }
               if (rs >= 0) best = fmaxf(best, epi[r * EPI_PITCH + ccol]);
             }
-            if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * C + cc * 32 + ccol, best);
+            if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + cc * 32 + ccol, best);
           }
           sat_named_barrier(1, 128);
         }
@@ -367,9 +396,9 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int C>
+template <int N>
 static size_t sat_smem_bytes() {
-  return (size_t)SAT_STAGES * (2 * SAT_ROWS * 128 + 2 * C * 128) + (size_t)SAT_ROWS * 33 * sizeof(float) + 2 * sizeof(SatRows) +
+  return (size_t)SAT_STAGES * (2 * SAT_ROWS * 128 + 2 * N * 128) + (size_t)SAT_ROWS * 33 * sizeof(float) + 2 * sizeof(SatRows) +
          sizeof(SatBars) + 64;
 }
 
@@ -379,10 +408,10 @@ static int launch_sa_tc(const float* T, const float* S, const int32_t* nbr, cons
                         cudaStream_t s) {
   const size_t smem = sat_smem_bytes<C>();
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "set abstraction (tensor cores): %zu bytes of shared memory", smem);
-  T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<C, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(n_obj, sms);  // objects are dealt round-robin to persistent CTAs
-  sa_edge_tc_kernel<C><<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj,
-                                                      reinterpret_cast<const uint4*>(w_img), b2, out);
+  sa_edge_tc_kernel<C, C, false><<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj,
+                                                                reinterpret_cast<const uint4*>(w_img), b2, out, C);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }
@@ -395,6 +424,25 @@ int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const 
   if (n_obj <= 0) return T2P_OK;
   if (C == 128) return launch_sa_tc<128>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, s);
   return launch_sa_tc<256>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, s);
+}
+
+// y[M / group, N] = max over groups of `group` consecutive rows of relu(x[M, 512] . W + b): the second layer of the global
+// abstraction MLP (512 -> 1024, pooled over the 32 points of an object).  x >= 0 is required (it is a ReLU output): the
+// producers apply relu(x - 0).  `out` must be zero-filled.  N is processed in column blocks of 256 (blockIdx.y).
+bool linear_groupmax_tc_supported(int K, int N) { return K == 512 && N % 256 == 0 && N >= 256; }
+
+int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, const float* bias, int N, int group, float* out,
+                              int sms, cudaStream_t s) {
+  if (M <= 0) return T2P_OK;
+  T2P_REQUIRE(linear_groupmax_tc_supported(K, N) && group >= 1, T2P_ERR_UNSUPPORTED, "linear_groupmax (tensor cores): K=%d N=%d", K, N);
+  const size_t smem = sat_smem_bytes<256>();
+  T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<512, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblocks = N / 256, tiles = (M + SAT_ROWS - 1) / SAT_ROWS;
+  dim3 grid(std::max(1, std::min(tiles, sms / nblocks)), nblocks);
+  sa_edge_tc_kernel<512, 256, true><<<grid, SAT_THREADS, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, 0, 0, group, M,
+                                                                   reinterpret_cast<const uint4*>(w_img), bias, out, N);
+  T2P_LAUNCH_CHECK();
+  return T2P_OK;
 }
 
 }  // namespace t2p

@@ -101,6 +101,12 @@ def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = Tru
             d.sa_l2_tc_off[l] = bb.add_raw_u32(_sa_tc_images(blob_w))
         else:
             d.sa_l2_tc_off[l] = -1
+    k, n = d.ga_l2.k, d.ga_l2.n
+    if k == 512 and n % 256 == 0:
+        blob_w = np.concatenate(bb.chunks)[d.ga_l2.w_off: d.ga_l2.w_off + k * n].astype(np.float64).reshape(k, n)
+        d.ga_l2_tc_off = bb.add_raw_u32(np.concatenate([_sa_tc_images(blob_w[:, j: j + 256]) for j in range(0, n, 256)]))
+    else:
+        d.ga_l2_tc_off = -1
     return d
 
 
@@ -111,16 +117,16 @@ def _sa_tc_images(w_kn: np.ndarray) -> np.ndarray:
     """w_kn [C, C] (= the BN-folded second local_nn layer as stored in the blob, [K, N]) -> uint32 words of the UMMA B-operand
     images streamed by ``sa_edge_tc_kernel``: [K chunk C/64][hi|lo][row n (output channel) C][64 fp16], value = fp16 split of
     2^8 * W[k = 64*chunk + e][n], the eight 16-byte units of every 128-byte row stored at (unit XOR (n & 7))."""
-    C = w_kn.shape[0]
-    assert w_kn.shape == (C, C) and C % 64 == 0
+    K, N = w_kn.shape  # the set-abstraction layers are square; the global-abstraction block is [512, 256]
+    assert K % 64 == 0 and N % 8 == 0
     w = w_kn.T * SA_TC_WSCALE                      # [n, k]
     hi = w.astype(np.float16)
     lo = (w - hi.astype(np.float64)).astype(np.float16)
-    n = np.arange(C)
+    n = np.arange(N)
     swz = np.arange(8)[None, :] ^ (n[:, None] & 7)  # physical unit v of row n holds logical unit v ^ (n & 7)
-    out = np.zeros((C // 64, 2, C, 8, 8), dtype=np.float16)
+    out = np.zeros((K // 64, 2, N, 8, 8), dtype=np.float16)
     for part, mat in enumerate((hi, lo)):
-        t = mat.reshape(C, C // 64, 8, 8).transpose(1, 0, 2, 3)  # [chunk, n, logical unit, elem]
+        t = mat.reshape(N, K // 64, 8, 8).transpose(1, 0, 2, 3)  # [chunk, n, logical unit, elem]
         out[:, part] = np.take_along_axis(t, swz[None, :, :, None], axis=2)
     return out.reshape(-1).view(np.uint32)
 

@@ -5,15 +5,15 @@
 //
 // Persistent CTAs (objects dealt round-robin), one work item = 128 consecutive edges of one object (edges packed centre by
 // centre; the packing, the
-// self-loop quirk and the gather indices are those of the fp32 kernel sa_edge_kernel, csrc/dense.cu).  Ten warps:
+// self-loop quirk and the gather indices are those of the fp32 kernel sa_edge_kernel, csrc/dense.cu).  Fourteen warps:
 //   warp 0      builds the row table of the NEXT item (prefix sum of the per-centre edge counts, one binary search per
 //               row, neighbour lookup) while the current one is processed;
 //   warp 1      issues the UMMAs: per 64-wide K chunk 4 K steps x 3 products of fp16 hi/lo splits (A_hi.W_hi + A_hi.W_lo +
 //               A_lo.W_hi, fp32 accumulation in TMEM; the dropped lo.lo term is ~2^-22 relative: fp32-grade, 1e-4 target);
-//   warps 2-5   produce the A operand: gather T_j (coalesced 32-byte pieces, 4 rows per warp instruction), subtract S_c,
+//   warps 2-9   produce the A operand: gather T_j (coalesced 32-byte pieces, 4 rows per warp instruction), subtract S_c,
 //               ReLU, split into fp16 hi/lo, store into the 128-byte-swizzled K-major UMMA layout; warp 2 also streams the
 //               W2 chunk (host-packed hi/lo images of 2^8.W2, cp.async.bulk) into the same stage;
-//   warps 6-9   epilogue: tcgen05.ld 32 columns at a time, *2^-8 + bias, ReLU, transpose through shared memory, running
+//   warps 10-13 epilogue: tcgen05.ld 32 columns at a time, *2^-8 + bias, ReLU, transpose through shared memory, running
 //               max over the rows of a centre (rows of a centre are contiguous), one atomicMax per (centre, column, tile).
 // Two pipeline stages (A chunk 32 KB + W chunk 2*C*128 B each), two TMEM accumulators (epilogue of item i overlaps the
 // MMAs of item i+1), two row tables.  No edge tensor in HBM, no scatter.
@@ -27,7 +27,9 @@ namespace t2p {
 using namespace sm100;
 
 constexpr int SAT_ROWS = 128;
-constexpr int SAT_THREADS = 320;
+constexpr int SAT_PROD_WARPS = 8;                       // A-operand producer warps (16 rows of a chunk each)
+constexpr int SAT_EPI_WARP0 = 2 + SAT_PROD_WARPS;        // first of the 4 epilogue warps
+constexpr int SAT_THREADS = 32 * (SAT_EPI_WARP0 + 4);
 constexpr int SAT_STAGES = 2;
 constexpr float SAT_WUNSCALE = 1.f / 256.f;
 
@@ -107,14 +109,14 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
 
   if (tid == 0) {
     for (int s = 0; s < SAT_STAGES; ++s) {
-      mbar_init(&bars->full[s], 5);  // 4 producer warps + the expect_tx arrive of the W loader
+      mbar_init(&bars->full[s], SAT_PROD_WARPS + 1);  // the producer warps + the expect_tx arrive of the W loader
       mbar_init(&bars->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], 4);  // one lane per epilogue warp
       mbar_init(&bars->rows_full[a], 1);
-      mbar_init(&bars->rows_empty[a], 9);  // one lane of each of the 9 consumer warps
+      mbar_init(&bars->rows_empty[a], SAT_PROD_WARPS + 5);  // one lane of each consumer warp (MMA, producers, epilogue)
     }
     mbar_fence_init();
   }
@@ -265,8 +267,8 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_empty[buf]);
     }
-  } else if (warp < 6) {
-    // ===== A producers: warp pw handles rows 32 pw .. 32 pw + 31; lane = (row sub-index 0..3, 8-column group 0..7) =====
+  } else if (warp < SAT_EPI_WARP0) {
+    // ===== A producers: warp pw handles rows 16 pw .. 16 pw + 15; lane = (row sub-index 0..3, 8-column group 0..7) =====
     const int pw = warp - 2;
     const int cg = lane & 7, rsub = lane >> 3;
     int stage = 0;
@@ -287,21 +289,22 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
             for (uint32_t off = 0; off < 2u * W_PART; off += 16384u) sat_bulk_load(dst + off, src + off, 16384u, &bars->full[stage]);
           }
           const int col0 = kc * 64 + cg * 8;
-          // all 16 T loads of this lane (8 rows x 32 bytes) are issued before the first use: one L2 round trip per chunk
+          // all T loads of this lane (4 rows x 32 bytes) are issued before the first use: one L2 round trip per chunk
           // instead of one per row; the S rows repeat from row to row (a centre has up to 33 edges) and hit L1
-          float4 tv[8][2];
-          int rsv[8];
+          constexpr int RPL = SAT_ROWS / SAT_PROD_WARPS / 4;  // rows per lane and chunk
+          float4 tv[RPL][2];
+          int rsv[RPL];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = pw * 32 + i * 4 + rsub;
+          for (int i = 0; i < RPL; ++i) {
+            const int r = pw * (SAT_ROWS / SAT_PROD_WARPS) + i * 4 + rsub;
             rsv[i] = rw->rowS[r];
             const float4* tp = reinterpret_cast<const float4*>(T + (size_t)rw->rowT[r] * C + col0);
             tv[i][0] = rsv[i] >= 0 ? __ldg(tp) : make_float4(0.f, 0.f, 0.f, 0.f);
             tv[i][1] = rsv[i] >= 0 ? __ldg(tp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = pw * 32 + i * 4 + rsub;
+          for (int i = 0; i < RPL; ++i) {
+            const int r = pw * (SAT_ROWS / SAT_PROD_WARPS) + i * 4 + rsub;
             const int rs = rsv[i];
             uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
             if (rs >= 0) {
@@ -340,10 +343,10 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       if (lane == 0) mbar_arrive(&bars->rows_empty[buf]);
     }
   } else {
-    // ===== epilogue: warps 6..9 own TMEM lane quadrants (warp & 3); 128 threads, named barrier 1 =====
+    // ===== epilogue: the last four warps own TMEM lane quadrants (warp & 3); 128 threads, named barrier 1 =====
     const int quad = warp & 3;
     const int row = quad * 32 + lane;          // TMEM lane = edge row of the tile
-    const int et = (warp - 6) * 32 + lane;     // 0..127: thread index inside the epilogue group
+    const int et = (warp - SAT_EPI_WARP0) * 32 + lane;     // 0..127: thread index inside the epilogue group
     const int ccol = et & 31, rgrp = et >> 5;  // column pass: column of the 32-chunk, group of 32 rows
     int nv = 0;
     for (int it = 0;; ++it) {

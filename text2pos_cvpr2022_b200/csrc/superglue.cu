@@ -14,41 +14,57 @@ constexpr int SG_RT = 24;  // rows per register chunk of the small GEMM
 constexpr int SG_HEADS = 4;
 
 // Y[r][c] (+)= sum_k Xa[r][k] W[k][c] + sum_k Xb[r][k] W[Ka+k][c] + bias[c], rows [0,RP) with RP % SG_RT == 0.
-// One thread per output column, all rows of a chunk in registers; W coalesced from global/L2.
+// One thread per (output column, slice of RT rows of a 24-row chunk), its rows in registers; W coalesced from global/L2 with
+// 16 loads in flight per thread.  The per-element arithmetic (k ascending, one fma chain) does not depend on the split.
+template <int RT>
+__device__ __forceinline__ void sg_gemm_rows(const float* __restrict__ Xa, int Ka, const float* __restrict__ Xb, int Kb, int ldx,
+                                             int RP, const float* __restrict__ W, const float* __restrict__ bias, int Nout,
+                                             float* __restrict__ Y, int ldy, bool relu, int c, int row_off) {
+  const float b = bias ? __ldg(bias + c) : 0.f;
+  for (int r0 = row_off; r0 < RP; r0 += SG_RT) {
+    float acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = b;
+    for (int seg = 0; seg < 2; ++seg) {
+      const float* X = seg ? Xb : Xa;
+      const int K = seg ? Kb : Ka;
+      const float* Wp = W + (size_t)(seg ? Ka : 0) * Nout + c;
+      if (K == 0) continue;
+      const float* xp = X + (size_t)r0 * ldx;
+#pragma unroll 4
+      for (int k = 0; k < K; k += 4) {
+        const float w0 = __ldg(Wp + (size_t)(k + 0) * Nout);
+        const float w1 = __ldg(Wp + (size_t)(k + 1) * Nout);
+        const float w2 = __ldg(Wp + (size_t)(k + 2) * Nout);
+        const float w3 = __ldg(Wp + (size_t)(k + 3) * Nout);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(xp + r * ldx + k);
+          acc[r] = fmaf(x.x, w0, acc[r]);
+          acc[r] = fmaf(x.y, w1, acc[r]);
+          acc[r] = fmaf(x.z, w2, acc[r]);
+          acc[r] = fmaf(x.w, w3, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) Y[(size_t)(r0 + r) * ldy + c] = relu ? fmaxf(acc[r], 0.f) : acc[r];
+  }
+}
+
 __device__ __forceinline__ void sg_gemm(const float* __restrict__ Xa, int Ka, const float* __restrict__ Xb, int Kb, int ldx,
                                         int RP, const float* __restrict__ W, const float* __restrict__ bias, int Nout,
                                         float* __restrict__ Y, int ldy, bool relu) {
-  for (int c = threadIdx.x; c < Nout; c += SG_THREADS) {
-    const float b = bias ? __ldg(bias + c) : 0.f;
-    for (int r0 = 0; r0 < RP; r0 += SG_RT) {
-      float acc[SG_RT];
-#pragma unroll
-      for (int r = 0; r < SG_RT; ++r) acc[r] = b;
-      for (int seg = 0; seg < 2; ++seg) {
-        const float* X = seg ? Xb : Xa;
-        const int K = seg ? Kb : Ka;
-        const float* Wp = W + (size_t)(seg ? Ka : 0) * Nout + c;
-        if (K == 0) continue;
-        const float* xp = X + (size_t)r0 * ldx;
-#pragma unroll 2
-        for (int k = 0; k < K; k += 4) {
-          const float w0 = __ldg(Wp + (size_t)(k + 0) * Nout);
-          const float w1 = __ldg(Wp + (size_t)(k + 1) * Nout);
-          const float w2 = __ldg(Wp + (size_t)(k + 2) * Nout);
-          const float w3 = __ldg(Wp + (size_t)(k + 3) * Nout);
-#pragma unroll
-          for (int r = 0; r < SG_RT; ++r) {
-            const float4 x = *reinterpret_cast<const float4*>(xp + r * ldx + k);
-            acc[r] = fmaf(x.x, w0, acc[r]);
-            acc[r] = fmaf(x.y, w1, acc[r]);
-            acc[r] = fmaf(x.z, w2, acc[r]);
-            acc[r] = fmaf(x.w, w3, acc[r]);
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < SG_RT; ++r) Y[(size_t)(r0 + r) * ldy + c] = relu ? fmaxf(acc[r], 0.f) : acc[r];
-    }
+  if (2 * Nout <= SG_THREADS) {
+    // narrow outputs (the D = 128 projections): two threads per column, 12 rows of every 24-row chunk each -- all 256
+    // threads work instead of half of them
+    const int per = SG_THREADS / 2;
+    const int half = threadIdx.x / per, t = threadIdx.x - half * per;
+    for (int c = t; c < Nout; c += per)
+      sg_gemm_rows<SG_RT / 2>(Xa, Ka, Xb, Kb, ldx, RP, W, bias, Nout, Y, ldy, relu, c, half * (SG_RT / 2));
+  } else {
+    for (int c = threadIdx.x; c < Nout; c += SG_THREADS)
+      sg_gemm_rows<SG_RT>(Xa, Ka, Xb, Kb, ldx, RP, W, bias, Nout, Y, ldy, relu, c, 0);
   }
 }
 

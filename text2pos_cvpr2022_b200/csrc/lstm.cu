@@ -566,7 +566,9 @@ int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32
     T2P_LAUNCH_CHECK();
     return T2P_OK;
   }
-  if (desc->whh_reg_off >= 0 && (H == 32 || H == 64 || H == 128 || H == 256) && desc->path != 1) {
+  // H == 32 would be a "cluster" of one CTA: the st.async hand-off needs a real cluster (compute-sanitizer flags it), so it takes
+  // the shared-memory kernel below
+  if (desc->whh_reg_off >= 0 && (H == 64 || H == 128 || H == 256) && desc->path != 1) {
     T2P_REQUIRE((size_t)desc->whh_reg_off + (size_t)2 * H * 4 * H <= w->n_floats, T2P_ERR_INVALID,
                 "lstm_encode: whh_reg outside the weight blob");
     Arena a(d_ws, ws_bytes);
@@ -575,8 +577,7 @@ int t2p_lstm_encode(const t2p_weights* w, const t2p_lstm_desc* desc, const int32
     const float* wr = wptr(w, desc->whh_reg_off);
     if (H == 256) T2P_TRY(lstm_reg_dispatch<256>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
     else if (H == 128) T2P_TRY(lstm_reg_dispatch<128>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
-    else if (H == 64) T2P_TRY(lstm_reg_dispatch<64>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
-    else T2P_TRY(lstm_reg_dispatch<32>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
+    else T2P_TRY(lstm_reg_dispatch<64>(xproj, wr, d_tokens, d_lengths, B, T, V, hfinal, s));
     lstm_finalize_kernel<<<(B + 7) / 8, 256, 0, s>>>(hfinal, B, H, normalize, d_out);
     T2P_LAUNCH_CHECK();
     return T2P_OK;

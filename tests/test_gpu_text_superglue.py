@@ -1,4 +1,4 @@
-"""GPU: text encoder (cluster LSTM) and SuperGlue head vs the reference's golden vectors and the oracle."""
+"""GPU: text encoder (tensor-core / register / shared-memory LSTM kernels) and SuperGlue head vs the reference's golden vectors and the oracle."""
 import numpy as np
 import pytest
 import torch

@@ -1,8 +1,8 @@
 """Drop-in for the reference's ``models/modules.py``: ``get_mlp`` and ``LanguageEncoder``.
 
 Same constructor signatures and ``state_dict`` keys (``word_embedding.weight``,
-``lstm.{weight,bias}_{ih,hh}_l0[_reverse]``); ``forward`` runs the sm_100a cluster LSTM kernel
-(``csrc/lstm.cu``) through ``t2p_lstm_encode`` instead of cuDNN.
+``lstm.{weight,bias}_{ih,hh}_l0[_reverse]``); ``forward`` runs the sm_100a LSTM kernels
+(tcgen05 recurrence ``csrc/lstm_tc.cu`` for H = 256, ``csrc/lstm.cu`` otherwise) through ``t2p_lstm_encode`` instead of cuDNN.
 """
 from typing import Dict, List, Sequence
 

@@ -8,7 +8,7 @@ runs, one D2H copy brings back scores, indices and the token counts (checked on 
 characters are tokenised by the Unicode-aware Python rules instead and skip the device tokeniser.
 
 The engine owns ``depth`` independent *slots* (staging buffers, workspaces, a stream and CUDA graphs each).  With
-``depth >= 2``, ``submit()`` / ``collect()`` keep several batches in flight: the host tokenises batch i+1 while the
+``depth >= 2``, ``submit()`` / ``collect()`` keep several batches in flight: the host stages batch i+1 while the
 GPU works on batch i, and the top-k of batch i overlaps the text encoder of batch i+1 on the idle SMs.
 """
 import collections

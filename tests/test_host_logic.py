@@ -226,3 +226,29 @@ def test_sa_tensor_core_images_layout_and_split():
             assert abs(hi + lo - v) <= 2.0 ** -21 * abs(v) + 1e-12
         assert np.array_equal(np.sort(img[:, 0].astype(np.float64).reshape(-1)),
                               np.sort((w * 256.0).astype(np.float16).astype(np.float64).reshape(-1)))
+
+
+def test_pointnet_pack_emits_tensor_core_images():
+    """pack_pointnet2: SA2 / SA3 (square, 128 / 256) and the second global-abstraction layer (512 -> 1024, four 256-wide column
+    blocks) get fp16 hi/lo images; SA1 (32 -> 64) does not.  Image (k, n) of column block j equals the folded weight the fp32
+    kernels read from the same blob."""
+    from text2pos_cvpr2022_b200.pointnet2 import PointNet2
+
+    pn = PointNet2(len(syn.KNOWN_CLASSES), len(syn.COLOR_NAMES), default_args(embed_dim=256))
+    syn.randomize_module_(pn, 3)
+    sd = cpu_state_dict(pn)
+    bb = packing.BlobBuilder()
+    d = packing.pack_pointnet2(bb, sd, "", True)
+    blob = bb.finish().numpy()
+    assert d.sa_l2_tc_off[0] == -1 and d.sa_l2_tc_off[1] >= 0 and d.sa_l2_tc_off[2] >= 0 and d.ga_l2_tc_off >= 0
+    K, N = d.ga_l2.k, d.ga_l2.n
+    assert (K, N) == (512, 1024)
+    w = blob[d.ga_l2.w_off: d.ga_l2.w_off + K * N].astype(np.float64).reshape(K, N)
+    img = blob[d.ga_l2_tc_off: d.ga_l2_tc_off + K * N].view(np.uint32).view(np.float16).reshape(N // 256, K // 64, 2, 256, 64)
+    for (k, n) in [(0, 0), (511, 1023), (70, 300), (129, 777)]:
+        j, nn = n // 256, n % 256
+        chunk, lu, e = k // 64, (k % 64) // 8, k % 8
+        pu = lu ^ (nn & 7)
+        v = w[k, n] * 256.0
+        hi, lo = float(img[j, chunk, 0, nn, pu * 8 + e]), float(img[j, chunk, 1, nn, pu * 8 + e])
+        assert hi == float(np.float16(v)) and abs(hi + lo - v) <= 2.0 ** -21 * abs(v) + 1e-12

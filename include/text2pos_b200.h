@@ -295,6 +295,50 @@ int t2p_superglue_forward(const t2p_weights* w, const t2p_superglue_desc* desc, 
                           int64_t* d_matches1, float* d_mscores0, float* d_mscores1, float* d_dbg_scores,
                           void* d_ws, size_t ws_bytes, t2p_stream stream);
 
+/* Gather variant for the cached fine stage (models/superglue_matcher.py:101-103 computes the object encodings
+ * of a cell anew for every query that retrieved it -- they are query independent): sample b reads block d_idx0[b] of a
+ * resident table d_desc0 [n_blocks0, M, D] and block d_idx1[b] of d_desc1 [n_blocks1, N, D] (NULL index = b). */
+int t2p_superglue_forward_gather(const t2p_weights* w, const t2p_superglue_desc* desc, const float* d_desc0,
+                                 const int64_t* d_idx0, const float* d_desc1, const int64_t* d_idx1, int B, int M, int N,
+                                 float* d_P, int64_t* d_matches0, int64_t* d_matches1, float* d_mscores0, float* d_mscores1,
+                                 float* d_dbg_scores, void* d_ws, size_t ws_bytes, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a1 / SURVEY 8f rank 2) batch_object_points on the device.  Replaces dataloading/kitti360pose/utils.py:89-110 with the
+ * transforms of evaluation/pipeline.py:290-293 (FixedPoints(P) with replacement + NormalizeScale) and the per-object
+ * np.mean calls of models/object_encoder.py:121-131.
+ * Packed raw cell store: d_raw_xyz / d_raw_rgb [total_points, 3] float32, d_obj_offsets [n_obj + 1] int64 (points of
+ * object o = [off[o], off[o+1])).  Sampling indices: d_choice [n_obj, P] int32 if given, else
+ * t2p_fixed_points_index(seed, obj_id_base + o, i, P, n_o) (splitmix64 counter hash; host-callable for the oracle).
+ * Outputs: d_pos / d_rgb [n_obj, P, 3] (pos centred on its float32 mean, scaled by float32((1/max|pos|) * 0.999999)),
+ * d_centers / d_mean_rgb [n_obj, 3] float32 = float64 means over the RAW points; optional d_centers64 [n_obj, 3] (the pose head
+ * reads float64 centres like the numpy original), optional d_choice_out [n_obj, P].
+ * ------------------------------------------------------------------------------------------------ */
+uint32_t t2p_fixed_points_index(uint64_t seed, uint64_t obj, uint32_t i, uint32_t P, uint32_t n);
+int t2p_batch_object_points(const float* d_raw_xyz, const float* d_raw_rgb, const int64_t* d_obj_offsets, int n_obj, int P,
+                            const int32_t* d_choice, uint64_t seed, int64_t obj_id_base, float* d_pos, float* d_rgb,
+                            float* d_centers, float* d_mean_rgb, double* d_centers64, int32_t* d_choice_out, t2p_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ *  pose head + accuracies on the device.
+ * t2p_pose_head replaces get_pos_in_cell (models/superglue_matcher.py:138-161) for B = Q*K (query, retrieved cell) samples:
+ *   d_matches0 [B, M] int64 (-1 = unmatched), d_offsets [n_off, N, 2] float32 with optional row index d_off_idx [B] (NULL: b),
+ *   d_centers [n_ctr, M, 2] float64 object centres (x, y) with optional block index d_cell_idx [B] (NULL: b)
+ *   -> d_pos_mean / d_pos_offsets [B, 2] float64 = mean over matched objects of centre (+ offset of its hint), (0.5, 0.5) if
+ *   nothing matched; d_confidence [B] int32 = number of matched objects (evaluation/pipeline.py:196).
+ * t2p_pose_accuracy replaces calc_sample_accuracies (evaluation/utils.py:31-54) and the mean-conf variant
+ *   (evaluation/pipeline.py:255-263): d_cell_idx [Q, K] indexes d_cell_origin [n_cells, 2] / d_cell_size [n_cells] (float64)
+ *   and d_cell_scene [n_cells]; d_pose_w [Q, 2] float64, d_pose_scene [Q]; h_top_k / h_threshs are HOST arrays (<= 8 each).
+ *   d_hits [3, Q, n_k, n_t] int32: [0] in-cell mean, [1] mean with offsets, [2] mean of the most confident cell (row ik = 0).
+ * ------------------------------------------------------------------------------------------------ */
+int t2p_pose_head(const int64_t* d_matches0, int B, int M, int N, const float* d_offsets, const int64_t* d_off_idx,
+                  const double* d_centers, const int64_t* d_cell_idx, double* d_pos_mean, double* d_pos_offsets,
+                  int32_t* d_confidence, t2p_stream stream);
+int t2p_pose_accuracy(const double* d_pos_mean, const double* d_pos_offsets, const int32_t* d_confidence,
+                      const int64_t* d_cell_idx, int Q, int K, const double* d_cell_origin, const double* d_cell_size,
+                      const int32_t* d_cell_scene, const double* d_pose_w, const int32_t* d_pose_scene, const int32_t* h_top_k,
+                      int n_k, const double* h_threshs, int n_t, int32_t* d_hits, t2p_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,4 +29,4 @@ Parity status (see DESIGN.md "Oracle"):
   ``models/object_encoder.py:61-142``, ``models/cell_retrieval.py:77-107``).
 """
 
-from . import mlp, pointnet, cells, text, retrieval, superglue  # noqa: F401
+from . import mlp, pointnet, cells, text, retrieval, superglue, models  # noqa: F401

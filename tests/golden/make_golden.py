@@ -125,7 +125,49 @@ def golden_retrieval(seed):
     np.savez_compressed(os.path.join(HERE, "retrieval.npz"), meta=json.dumps(metas), **out)
 
 
+def golden_pipeline(seed):
+    """Run the reference's OWN ``evaluation/pipeline.py`` ``run_coarse`` / ``run_fine`` (imported unmodified, with the
+    compat layer standing in for easydict / torch_geometric.transforms) over the CPU oracle models on a small synthetic scene;
+    store retrievals, accuracy dicts and the matcher outputs.  ``training.coarse.eval_epoch`` (which evaluation.pipeline
+    imports) resolves to this repository's CUDA drop-in, so the CPU restatement ``oracle.models.eval_epoch`` is patched in."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    import pipeline_common as pc
+    from text2pos_cvpr2022_b200 import compat
+
+    compat.install()
+    if REF not in sys.path:
+        sys.path.append(REF)  # after the repository: models.* / training.coarse resolve to the B200 modules
+    import evaluation.pipeline as ref
+    from datapreparation.kitti360pose.imports import Object3d
+
+    ds, loader = pc.scene(seed)
+    args = pc.pipeline_args()
+    cm, csd = pc.coarse_state_dict()
+    fm, fsd = pc.fine_state_dict()
+    coarse = oracle.models.OracleCoarseModel(csd, cm.language_encoder.known_words)
+    fine = pc.RecordingModel(oracle.models.OracleFineModel(fsd, fm.language_encoder.known_words))
+    ref.eval_epoch_retrieval = oracle.models.eval_epoch
+    retrievals, coarse_acc = ref.run_coarse(coarse, loader, args)
+    ref.transform = pc.reference_transform()
+    np.random.seed(seed)
+    acc_mean, acc_off, acc_conf = ref.run_fine(fine, retrievals, loader, args)
+    flat = lambda a: np.array([[float(a[k][t]) for t in sorted(a[k])] for k in sorted(a)])
+    np.savez_compressed(
+        os.path.join(HERE, "pipeline_small.npz"),
+        meta=json.dumps(dict(seed=seed, n_cells=len(ds.all_cells), n_poses=len(ds.all_poses), top_k=args.top_k, threshs=args.threshs,
+                             padding="Object3d.create_padding on np.random.seed(seed)", object3d=str(Object3d))),
+        retrievals=np.array([list(r) for r in retrievals]), coarse_acc=flat(coarse_acc), acc_mean=flat(acc_mean),
+        acc_offset=flat(acc_off), acc_mean_conf=flat(acc_conf),
+        matches0=np.stack([o["matches0"] for o in fine.outputs]), offsets=np.stack([o["offsets"] for o in fine.outputs]),
+        P=np.stack([o["P"] for o in fine.outputs]),
+    )
+
+
 def main():
+    if "--pipeline-only" in sys.argv:
+        golden_pipeline(seed=11)
+        return
     ref_modules, ref_superglue = _import_reference()
     torch.manual_seed(0)
     golden_superglue(ref_superglue, "fine", D=128, num_layers=6, iters=50, B=8, M=16, N=6, seed=11, gain=0.4, peaky=5.0)
@@ -134,6 +176,7 @@ def main():
     golden_language_encoder(ref_modules, "fine", D=128, n_queries=6, n_hints=1, seed=22)
     golden_get_mlp(ref_modules, seed=31)
     golden_retrieval(seed=41)
+    golden_pipeline(seed=11)
     print("golden vectors written to", HERE)
 
 

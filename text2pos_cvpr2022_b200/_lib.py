@@ -148,6 +148,14 @@ PROTOTYPES = {
         _I,
         [_P, C.POINTER(SuperGlueDesc), _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
     ),
+    "t2p_superglue_forward_gather": (
+        _I,
+        [_P, C.POINTER(SuperGlueDesc), _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    ),
+    "t2p_fixed_points_index": (C.c_uint32, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "t2p_batch_object_points": (_I, [_P, _P, _P, _I, _I, _P, C.c_uint64, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "t2p_pose_head": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "t2p_pose_accuracy": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, C.POINTER(C.c_int32), _I, C.POINTER(C.c_double), _I, _P, _P]),
 }
 
 _lock = threading.Lock()

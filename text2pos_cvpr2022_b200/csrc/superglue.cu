@@ -74,8 +74,8 @@ struct SgLayerPtrs {
 
 __global__ void __launch_bounds__(SG_THREADS, 1)
 superglue_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_superglue_desc d,
-                 const float* __restrict__ desc0, const float* __restrict__ desc1, int M, int N, int RP,
-                 float* __restrict__ outP, int64_t* __restrict__ matches0, int64_t* __restrict__ matches1,
+                 const float* __restrict__ desc0, const float* __restrict__ desc1, const int64_t* __restrict__ idx0,
+                 const int64_t* __restrict__ idx1, int M, int N, int RP, float* __restrict__ outP, int64_t* __restrict__ matches0, int64_t* __restrict__ matches1,
                  float* __restrict__ mscores0, float* __restrict__ mscores1, float* __restrict__ dbg_scores) {
   extern __shared__ __align__(16) float sg_smem[];
   const int D = d.dim, R = M + N, dh = D / SG_HEADS;
@@ -93,11 +93,13 @@ superglue_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_sup
   int* I0 = reinterpret_cast<int*>(Vv + (N + 1));  // [M] argmax per row, [N] argmax per column
   int* I1 = I0 + M;
 
+  // gather variant: sample b reads block idx0[b] of a resident table of object encodings and block idx1[b] of the hint encodings
+  const size_t b0 = idx0 ? (size_t)idx0[b] : (size_t)b, b1 = idx1 ? (size_t)idx1[b] : (size_t)b;
   for (int t = tid; t < RP * D; t += SG_THREADS) {
     const int r = t / D, c = t - r * D;
     float v = 0.f;
-    if (r < M) v = __ldg(desc0 + ((size_t)b * M + r) * D + c);
-    else if (r < R) v = __ldg(desc1 + ((size_t)b * N + (r - M)) * D + c);
+    if (r < M) v = __ldg(desc0 + (b0 * M + r) * D + c);
+    else if (r < R) v = __ldg(desc1 + (b1 * N + (r - M)) * D + c);
     X[t] = v;
   }
   __syncthreads();
@@ -284,6 +286,14 @@ size_t t2p_superglue_workspace(int B, int M, int N, int D) {
 int t2p_superglue_forward(const t2p_weights* w, const t2p_superglue_desc* desc, const float* d_desc0, const float* d_desc1,
                           int B, int M, int N, float* d_P, int64_t* d_matches0, int64_t* d_matches1, float* d_mscores0,
                           float* d_mscores1, float* d_dbg_scores, void* d_ws, size_t ws_bytes, t2p_stream stream) {
+  return t2p_superglue_forward_gather(w, desc, d_desc0, nullptr, d_desc1, nullptr, B, M, N, d_P, d_matches0, d_matches1, d_mscores0,
+                                      d_mscores1, d_dbg_scores, d_ws, ws_bytes, stream);
+}
+
+int t2p_superglue_forward_gather(const t2p_weights* w, const t2p_superglue_desc* desc, const float* d_desc0,
+                                 const int64_t* d_idx0, const float* d_desc1, const int64_t* d_idx1, int B, int M, int N,
+                                 float* d_P, int64_t* d_matches0, int64_t* d_matches1, float* d_mscores0, float* d_mscores1,
+                                 float* d_dbg_scores, void* d_ws, size_t ws_bytes, t2p_stream stream) {
   T2P_REQUIRE(w && desc && d_desc0 && d_desc1 && d_P && d_matches0 && d_matches1 && d_mscores0 && d_mscores1,
               T2P_ERR_INVALID, "superglue: null argument");
   if (B <= 0) return T2P_OK;
@@ -308,7 +318,7 @@ int t2p_superglue_forward(const t2p_weights* w, const t2p_superglue_desc* desc, 
   (void)d_ws; (void)ws_bytes;
   cudaStream_t s = as_stream(stream);
   T2P_CUDA(cudaFuncSetAttribute(superglue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  superglue_kernel<<<B, SG_THREADS, smem, s>>>(w->d_blob, *desc, d_desc0, d_desc1, M, N, RP, d_P, d_matches0, d_matches1,
+  superglue_kernel<<<B, SG_THREADS, smem, s>>>(w->d_blob, *desc, d_desc0, d_desc1, d_idx0, d_idx1, M, N, RP, d_P, d_matches0, d_matches1,
                                                d_mscores0, d_mscores1, d_dbg_scores);
   T2P_LAUNCH_CHECK();
   return T2P_OK;

@@ -120,12 +120,33 @@ class PointBatch:
 # ----------------------------------------------------------------------------------------------
 def fixed_points_normalize(xyz: np.ndarray, rgb: np.ndarray, rng: np.random.Generator, num: int = NUM_POINTS):
     """``Compose([FixedPoints(num), NormalizeScale()])``: resample WITH replacement, centre, scale to (-1,1)."""
-    choice = rng.integers(0, xyz.shape[0], size=num)
+    return fixed_points_normalize_idx(xyz, rgb, rng.integers(0, xyz.shape[0], size=num))
+
+
+def fixed_points_normalize_idx(xyz: np.ndarray, rgb: np.ndarray, choice: np.ndarray):
+    """The same transform for given sampling indices (what ``t2p_batch_object_points`` computes on the device: float32 mean
+    accumulated row by row, scale = float32((1 / max|pos|) * 0.999999))."""
     pos = xyz[choice].astype(np.float32)
     col = rgb[choice].astype(np.float32)
     pos = pos - pos.mean(axis=0, keepdims=True)
     scale = np.float32((1.0 / max(float(np.abs(pos).max()), 1e-12)) * 0.999999)
     return pos * scale, col
+
+
+def batch_object_points_idx(objects: Sequence["SynthObject3d"], seed: int, obj_id0: int, num: int = NUM_POINTS) -> "PointBatch":
+    """``batch_object_points`` with the counter-based sampling of the device data path (``cell_store.fixed_points_indices``):
+    object ``i`` of the list is global object ``obj_id0 + i``."""
+    from .cell_store import fixed_points_indices
+
+    n_pts = np.array([np.asarray(o.xyz).reshape(-1, 3).shape[0] for o in objects])
+    choice = fixed_points_indices(seed, obj_id0 + np.arange(len(objects)), n_pts, num)
+    xs, ps = [], []
+    for o, ch in zip(objects, choice):
+        pos, col = fixed_points_normalize_idx(np.asarray(o.xyz, dtype=np.float32), np.asarray(o.rgb, dtype=np.float32), ch)
+        ps.append(pos)
+        xs.append(col)
+    batch = np.repeat(np.arange(len(objects)), num)
+    return PointBatch(torch.from_numpy(np.concatenate(xs)), torch.from_numpy(np.concatenate(ps)), torch.from_numpy(batch))
 
 
 def synth_object(rng: np.random.Generator, kind: Optional[int] = None, n_src: Optional[int] = None, obj_id: int = 0):
@@ -146,10 +167,12 @@ def synth_object(rng: np.random.Generator, kind: Optional[int] = None, n_src: Op
     return SynthObject3d(obj_id, xyz, rgb, label)
 
 
-def synth_cell(rng: np.random.Generator, idx: int, n_obj: Optional[int] = None, scene: str = "0010", cell_size=30.0):
+def synth_cell(rng: np.random.Generator, idx: int, n_obj: Optional[int] = None, scene: str = "0010", cell_size=30.0,
+               origin: Optional[np.ndarray] = None):
     n_obj = int(rng.integers(6, 17)) if n_obj is None else n_obj
     objects = [synth_object(rng, obj_id=i) for i in range(n_obj)]
-    origin = np.array([rng.random() * 1000.0, rng.random() * 1000.0, 0.0])
+    if origin is None:
+        origin = np.array([rng.random() * 1000.0, rng.random() * 1000.0, 0.0])
     bbox = np.concatenate([origin, origin + cell_size])
     return SynthCell(idx, scene, objects, cell_size, bbox)
 
@@ -234,11 +257,26 @@ def synth_packed_cells(seed: int, n_cells: int, n_obj: Optional[int] = None) -> 
 # ----------------------------------------------------------------------------------------------
 # text
 # ----------------------------------------------------------------------------------------------
-def synth_hint(rng: np.random.Generator) -> str:
+class SynthDescription:
+    """Duck type of ``DescriptionBestCell`` (imports.py:125-175): the three fields the hint template reads."""
+
+    def __init__(self, direction: str, object_color_text: str, object_label: str):
+        self.direction, self.object_color_text, self.object_label = direction, object_color_text, object_label
+
+    def hint(self) -> str:
+        """``Kitti360BaseDataset.create_hint_description`` template (dataloading/kitti360pose/base.py:63-65)."""
+        return f"The pose is {self.direction} of a {self.object_color_text} {self.object_label}."
+
+
+def synth_description(rng: np.random.Generator) -> SynthDescription:
     d = DIRECTIONS[int(rng.integers(0, len(DIRECTIONS)))]
     c = COLOR_NAMES[int(rng.integers(0, len(COLOR_NAMES)))]
     k = KNOWN_CLASSES[int(rng.integers(0, len(KNOWN_CLASSES) - 1))]
-    return f"The pose is {d} of a {c} {k}."
+    return SynthDescription(d, c, k)
+
+
+def synth_hint(rng: np.random.Generator) -> str:
+    return synth_description(rng).hint()
 
 
 def synth_hints(seed: int, n_queries: int, n_hints: int = NUM_HINTS) -> List[List[str]]:
@@ -257,10 +295,14 @@ def synth_queries(seed: int, n_queries: int, n_hints: int = NUM_HINTS) -> List[s
 class SynthPose:
     """Duck type of the reference ``Pose`` (imports.py:178-218): world position, its cell, six hint descriptions."""
 
-    def __init__(self, pose_w: np.ndarray, cell_id: str, hints: List[str]):
+    def __init__(self, pose_w: np.ndarray, cell_id: str, descriptions: List[SynthDescription]):
         self.pose_w = pose_w
         self.cell_id = cell_id
-        self.descriptions = hints
+        self.descriptions = descriptions
+
+    @property
+    def hints(self) -> List[str]:
+        return [d.hint() for d in self.descriptions]
 
 
 class SynthCellDataset:
@@ -285,14 +327,25 @@ class SynthCoarseDataset:
     """``Kitti360CoarseDatasetMulti`` stand-in: ``n_poses`` poses spread over ``n_cells`` cells of one scene; the text of a
     pose is its six template hints joined by a space (dataloading/kitti360pose/cells.py:82)."""
 
-    def __init__(self, seed: int, n_cells: int, n_poses: int):
+    def __init__(self, seed: int, n_cells: int, n_poses: int, scenes: Sequence[str] = ("0010",), grid_stride: Optional[float] = None,
+                 max_objects: Optional[int] = None):
+        """``scenes``: cells are dealt round-robin to these scene names (ids ``"<scene>_<idx>"``); ``grid_stride``: lay the
+        cells of a scene out on a square grid with this stride in metres (KITTI360Pose cells overlap: stride 10, size 30)
+        instead of scattering them; ``max_objects``: upper bound of the objects per cell (default 16; more exercises the
+        cut-off of the top-k dataset)."""
         rng = np.random.default_rng(seed)
-        self.all_cells = [synth_cell(rng, i) for i in range(n_cells)]
+        self.all_cells = []
+        side = int(np.ceil(np.sqrt(max(1, n_cells / max(1, len(scenes))))))
+        for i in range(n_cells):
+            scene, j = scenes[i % len(scenes)], i // len(scenes)
+            origin = None if grid_stride is None else np.array([(j % side) * grid_stride, (j // side) * grid_stride, 0.0])
+            n_obj = None if max_objects is None else int(rng.integers(6, max_objects + 1))
+            self.all_cells.append(synth_cell(rng, i, n_obj, scene=scene, origin=origin))
         self.all_poses = []
         for _ in range(n_poses):
             c = self.all_cells[int(rng.integers(0, n_cells))]
             pose_w = c.bbox_w[0:3] + rng.random(3) * c.cell_size
-            self.all_poses.append(SynthPose(pose_w, c.id, [synth_hint(rng) for _ in range(NUM_HINTS)]))
+            self.all_poses.append(SynthPose(pose_w, c.id, [synth_description(rng) for _ in range(NUM_HINTS)]))
         self._cell_dataset = SynthCellDataset(self.all_cells, seed)
 
     def __len__(self):
@@ -300,7 +353,7 @@ class SynthCoarseDataset:
 
     def __getitem__(self, idx: int):
         pose = self.all_poses[idx]
-        return {"poses": pose, "texts": " ".join(pose.descriptions), "cell_ids": pose.cell_id}
+        return {"poses": pose, "texts": " ".join(pose.hints), "cell_ids": pose.cell_id}
 
     def get_cell_dataset(self):
         return self._cell_dataset

@@ -1,0 +1,202 @@
+"""GPU: the callers either side of the hot path -- device ``batch_object_points``, cached fine stage
+(rank 1), pose head + accuracies (rank 3) -- and BASELINE config 5 (coarse -> fine pipeline on a synthetic KITTI360Pose-shaped
+scene) through the CUDA modules vs the CPU oracle models through the same pipeline logic; plus the independent end-to-end
+top-10 check of config 1 (oracle encoders -> float64 ranking vs CUDA encoders -> CUDA top-k)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import pipeline_common as pc
+from conftest import cpu_state_dict
+from text2pos_cvpr2022_b200 import pipeline_eval as pe, synthetic as syn
+from text2pos_cvpr2022_b200.cell_store import CellStore, build_cell_database, fixed_points_indices
+from text2pos_cvpr2022_b200.retrieval import CellDatabase
+from text2pos_cvpr2022_b200.superglue_matcher import pose_head
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat(a):
+    return np.array([[float(a[k][t]) for t in sorted(a[k])] for k in sorted(a)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f2: device batch_object_points
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("given_choice", [False, True])
+def test_batch_object_points_matches_host_transform(given_choice):
+    """pos / rgb bit-exact vs ``fixed_points_normalize_idx`` for the same indices (the same indices the host mirror of the
+    counter hash gives); centre / mean colour within one float32 ulp of the float64 numpy means."""
+    cells, objects, _ = syn.synth_cells(21, 9)
+    # edge cases: a 1-point object, an 8-point padding object, a big one
+    objects[0][0] = syn.SynthObject3d(0, np.array([[0.25, 0.5, 0.75]]), np.array([[0.1, 0.2, 0.3]]), "box")
+    objects[1][0] = syn.SynthObject3d.create_padding(np.random.default_rng(1))
+    objects[2][0] = syn.synth_object(np.random.default_rng(2), kind=2, n_src=5000)
+    for c, o in zip(cells, objects):
+        c.objects = o
+    st = CellStore.from_cells(cells).to("cuda")
+    n_pts = (st.obj_offsets[1:] - st.obj_offsets[:-1]).cpu().numpy()
+    seed = 77
+    choice = fixed_points_indices(seed, np.arange(st.num_objects), n_pts)
+    if given_choice:
+        rng = np.random.default_rng(3)
+        choice = np.stack([rng.integers(0, n, size=256) for n in n_pts]).astype(np.int32)
+    got, ctr64, ch = st.batch_object_points(seed=seed, choice=torch.from_numpy(choice) if given_choice else None, return_extras=True)
+    np.testing.assert_array_equal(ch.cpu().numpy(), choice)
+    flat = [o for cell in objects for o in cell]
+    ref_pos, ref_rgb = zip(*[syn.fixed_points_normalize_idx(np.asarray(o.xyz, np.float32), np.asarray(o.rgb, np.float32), c)
+                             for o, c in zip(flat, choice)])
+    np.testing.assert_array_equal(got.pos.cpu().numpy(), np.stack(ref_pos))
+    np.testing.assert_array_equal(got.rgb.cpu().numpy(), np.stack(ref_rgb))
+    ctr = np.array([np.asarray(o.xyz, np.float32).astype(np.float64).mean(0) for o in flat])
+    col = np.array([np.asarray(o.rgb, np.float32).astype(np.float64).mean(0) for o in flat])
+    np.testing.assert_allclose(ctr64.cpu().numpy(), ctr, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(got.centers.cpu().numpy(), ctr, rtol=0, atol=6e-8)
+    np.testing.assert_allclose(got.mean_rgb.cpu().numpy(), col, rtol=0, atol=6e-8)
+    assert got.cell_offsets.tolist() == st.cell_offsets.tolist()
+    # a slice of cells resamples exactly as inside the whole store (global object ids)
+    part = st.batch_object_points(3, 6, seed=seed, choice=None) if not given_choice else None
+    if part is not None:
+        o0, o1 = int(st.cell_offsets[3]), int(st.cell_offsets[6])
+        assert torch.equal(part.pos, got.pos[o0:o1])
+
+
+def test_db_build_from_store_equals_the_host_packed_path(coarse_model):
+    """raw store -> batch_object_points kernel -> encoders == host-side packing of the same resampled points -> encoders."""
+    ds, _ = pc.scene(11)
+    st = CellStore.from_cells(ds.all_cells).to("cuda")
+    emb = build_cell_database(coarse_model, st, seed=5, cells_per_call=6)
+    off = st.cell_offsets.cpu().numpy()
+    objects = [c.objects for c in ds.all_cells]
+    points = [syn.batch_object_points_idx(o, 5, int(off[i])) for i, o in enumerate(objects)]
+    ref = coarse_model.encode_objects(objects, points)
+    np.testing.assert_allclose(emb.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=2e-6)
+    # sharded build: every rank's block of the raw cells gives its block of the embeddings, born in place
+    parts = [build_cell_database(coarse_model, CellStore.from_cells(ds.all_cells).shard(r, 3).to("cuda"), seed=5) for r in range(3)]
+    assert [p.shape[0] for p in parts] == [5, 5, 4]
+    # (object ids restart per shard store, so resampling differs from the global store: shards are built with obj_id_base)
+    sh = CellStore.from_cells(ds.all_cells).shard(1, 3).to("cuda")
+    cells1 = sh.batch_object_points(seed=5, obj_id_base=int(off[5]))
+    np.testing.assert_allclose(coarse_model.encode_cells_packed(cells1).cpu().numpy(), emb[5:10].cpu().numpy(), rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f3: pose head + accuracies
+# ---------------------------------------------------------------------------------------------------------------
+def test_pose_head_equals_get_pos_in_cell():
+    rng = np.random.default_rng(0)
+    B, M, N = 300, 16, 6
+    matches = rng.integers(-1, N, size=(B, M))
+    matches[rng.random((B, M)) < 0.6] = -1
+    matches[0] = -1  # nothing matched -> (0.5, 0.5)
+    offsets = rng.normal(size=(B, N, 2)).astype(np.float32) * 0.1
+    centers = rng.random((B, M, 2))
+    pm, po, conf = pose_head(torch.from_numpy(matches).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(centers).cuda())
+
+    class O:
+        def __init__(self, c):
+            self.c = c
+
+        def get_center(self):
+            return self.c
+
+    for b in range(B):
+        objs = [O(np.array([centers[b, i, 0], centers[b, i, 1], 0.0])) for i in range(M)]
+        ref_m = oracle.models.get_pos_in_cell(objs, matches[b], np.zeros_like(offsets[b]))
+        ref_o = oracle.models.get_pos_in_cell(objs, matches[b], offsets[b])
+        assert np.array_equal(pm[b].cpu().numpy(), ref_m) and np.array_equal(po[b].cpu().numpy(), ref_o), b
+    assert conf.cpu().tolist() == (matches >= 0).sum(1).tolist()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 5: coarse -> fine pipeline, CUDA modules vs oracle models
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def matching_fine_model():
+    m, sd = pc.fine_state_dict()
+    return m.to("cuda"), sd
+
+
+def test_pipeline_config5_cuda_vs_oracle(coarse_model, matching_fine_model):
+    fine_model, fsd = matching_fine_model
+    ds, loader = pc.scene(11)
+    args = pc.pipeline_args()
+    # CUDA: drop-in path
+    retrievals, coarse_acc = pe.run_coarse(coarse_model, loader, args)
+    acc = pe.run_fine(fine_model, retrievals, loader, args, return_details=True)
+    # oracle models through the same pipeline logic
+    o_coarse = oracle.models.OracleCoarseModel(cpu_state_dict(coarse_model), coarse_model.language_encoder.known_words)
+    o_fine = oracle.models.OracleFineModel(fsd, fine_model.language_encoder.known_words)
+    o_retr, o_coarse_acc = pe.run_coarse(o_coarse, loader, args, eval_epoch_fn=oracle.models.eval_epoch)
+    assert [list(r) for r in retrievals] == [list(r) for r in o_retr]
+    np.testing.assert_array_equal(_flat(coarse_acc), _flat(o_coarse_acc))
+    o_acc = pe.run_fine(o_fine, o_retr, loader, args, return_details=True)
+    np.testing.assert_array_equal(acc[3]["matches"], o_acc[3]["matches"])
+    assert (acc[3]["matches"] >= 0).sum() > 50
+    np.testing.assert_allclose(acc[3]["offsets"], o_acc[3]["offsets"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(acc[3]["pos_offsets"], o_acc[3]["pos_offsets"], rtol=0, atol=1e-4)
+    for a, b in zip(acc[:3], o_acc[:3]):
+        np.testing.assert_array_equal(_flat(a), _flat(b))
+
+    # cached fine stage (host-built cache): the same matches / positions / accuracies as the drop-in path
+    cached = pe.run_fine_cached(fine_model, retrievals, loader, args, queries_per_call=4, return_details=True)
+    np.testing.assert_array_equal(cached[3]["matches"], acc[3]["matches"])
+    np.testing.assert_array_equal(cached[3]["confidences"], acc[3]["confidences"])
+    np.testing.assert_allclose(cached[3]["offsets"], acc[3]["offsets"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(cached[3]["pos_mean"], acc[3]["pos_mean"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(cached[3]["pos_offsets"], acc[3]["pos_offsets"], rtol=0, atol=1e-6)
+    for a, b in zip(cached[:3], acc[:3]):
+        np.testing.assert_array_equal(_flat(a), _flat(b))
+
+    # cache built on the device from a padded raw cell store (no host loop over objects)
+    store = CellStore.from_cells(ds.all_cells, args.pad_size, lambda cell: pe.seeded_padding_factory(0, cell.id)).to("cuda")
+    cache = pe.FineCellCache.from_store(fine_model, store, seed=0)
+    host_cache = pe.FineCellCache(fine_model, ds.all_cells, args)
+    np.testing.assert_allclose(cache.obj_enc.cpu().numpy(), host_cache.obj_enc.cpu().numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(cache.centers.cpu().numpy(), host_cache.centers.cpu().numpy(), rtol=0, atol=1e-7)
+    dev = pe.run_fine_cached(fine_model, retrievals, loader, args, cache=cache, return_details=True)
+    np.testing.assert_array_equal(dev[3]["matches"], acc[3]["matches"])
+    for a, b in zip(dev[:3], acc[:3]):
+        np.testing.assert_array_equal(_flat(a), _flat(b))
+
+    # replicas: two halves of the queries combine to the same tables (fine stage = replicas only)
+    n = len(retrievals)
+    halves = [pe.run_fine_cached(fine_model, retrievals, loader, args, cache=cache, query_range=r)[3]
+              for r in (range(0, n // 2), range(n // 2, n))]
+    for a, b in zip(pe.combine_replica_sums(halves, args.top_k, args.threshs), acc[:3]):
+        np.testing.assert_array_equal(_flat(a), _flat(b))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 1 end to end, both sides independent
+# ---------------------------------------------------------------------------------------------------------------
+def test_config1_topk_ids_end_to_end_independent(coarse_model):
+    """BASELINE configs[0]: 128 synthetic cells, top-10.  Oracle text + cell encoders -> float64 ranking on one side, CUDA text
+    + cell encoders -> CUDA top-k on the other; NOTHING of the GPU side feeds the oracle side.  A query is compared when the
+    oracle's own ranking is tie-free at the resolution of the 1e-4 embedding tolerance (gap between consecutive scores of its
+    top-11 > 1e-5, far above the ~1e-7 difference of the embeddings); the fixture must leave most queries comparable."""
+    cells, objects, points = syn.synth_cells(0, 128)
+    texts = syn.synth_queries(1, 16)
+    sd = cpu_state_dict(coarse_model)
+    packed = syn.pack_cells(objects, points)
+    sl = packed.cell_slices()
+    with torch.no_grad():
+        ref_cells = oracle.cells.encode_objects(sd, [packed.rgb[a:b] for a, b in sl], [packed.pos[a:b] for a, b in sl],
+                                                packed.centers, packed.mean_rgb).numpy()
+        ref_text = oracle.text.encode_text(sd, texts, coarse_model.language_encoder.known_words).numpy()
+    ref_idx, ref_scores = oracle.retrieval.topk(ref_cells, ref_text, 11)
+
+    cell_enc = coarse_model.encode_objects(objects, points)
+    text_enc = coarse_model.encode_text(texts)
+    idx, _ = CellDatabase(cell_enc, [c.id for c in cells]).topk(text_enc, 10)
+    idx = idx.cpu().numpy()
+
+    gaps = -np.diff(ref_scores, axis=1)  # [Q, 10] consecutive gaps of the oracle's top-11
+    comparable = gaps.min(axis=1) > 1e-5
+    assert comparable.sum() >= 12, f"fixture too tie-prone: only {comparable.sum()} of 16 queries comparable"
+    for q in np.nonzero(comparable)[0]:
+        assert idx[q].tolist() == ref_idx[q, :10].tolist(), q
+    # the remaining queries still return the same SET up to the tied pair
+    for q in np.nonzero(~comparable)[0]:
+        assert len(set(idx[q].tolist()) ^ set(ref_idx[q, :10].tolist())) <= 2

@@ -259,7 +259,7 @@ def main_b200(args):
 
     depth = max(1, args.depth)  # batches in flight (one stream per slot)
     eng = OnlineRetrievalEngine(model, base, k=TOPK, max_batch=B_QUERIES, max_tokens=T, idx_base=lo, depth=depth,
-                                lstm_clusters=args.lstm_clusters)
+                                lstm_clusters=args.lstm_clusters, scan_ctas=args.scan_ctas)
     sharded = ShardedOnlineRetrievalEngine(eng, exchange=args.exchange) if world > 1 else None
     user = sharded if sharded is not None else eng
     q_per_step = B_QUERIES * world  # whole job
@@ -515,7 +515,7 @@ def main_b200(args):
         "config": config_dict(world), "parallelism": par,
         "roofline": dominant, "roofline_other": other, "roofline_network": roof_net, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": (OnlineRetrievalEngine.KERNELS_PER_STEP + ((5 if args.exchange == "p2p" else 1) if world > 1 else 0)) * K * world,
-        "pipeline": {"depth": depth, "lstm_clusters_per_direction": eng.lstm_desc.max_groups or 7, "serial_ms_per_step": serial_ms_step, "serial_value": q_per_step / (serial_ms_step * 1e-3),
+        "pipeline": {"depth": depth, "lstm_clusters_per_direction": eng.lstm_desc.max_groups or 7, "scan_ctas": eng.scan_ctas or "one per SM", "serial_ms_per_step": serial_ms_step, "serial_value": q_per_step / (serial_ms_step * 1e-3),
                      "cuda_graphs": graphs,
                      "note": "value/ms_per_step: `depth` batches in flight on separate streams, one CUDA-graph replay per step; "
                              "roofline kernel times: serial pass of direct launches"},
@@ -596,6 +596,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rows", action="store_true", help="skip the secondary measurements (DB build, cached fine stage)")
     ap.add_argument("--lstm-clusters", type=int, default=None, help="LSTM clusters per direction (default: 7 if depth == 1, 2 if depth < 8, else 1)")
+    ap.add_argument("--scan-ctas", type=int, default=None, help="top-k scan CTAs (default: one per SM if depth == 1, else 40)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange: own peer-memory kernels or NCCL")
     ap.add_argument("--depth", type=int, default=12, help="batches in flight (one stream per slot)")
     args = ap.parse_args()

@@ -81,6 +81,8 @@ int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, 
  *   d_stats:        optional device int32[2]: [0] += queries certified on the tensor path, [1] += queries rescanned. */
 #define T2P_RETRIEVE_FORCE_GENERIC 1 /* always use the CUDA-core scan */
 #define T2P_RETRIEVE_FORCE_RESCAN 2  /* tensor path, but treat every query as uncertified (tests the rescan) */
+#define T2P_RETRIEVE_MAX_CTAS(n) (((n) & 0xff) << 8) /* tensor path: at most n scan CTAs (0 = one per SM).  Fewer CTAs = less
+                                                        SM-time per batch at more latency: for servers with batches in flight */
 int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
                          const float* d_db_norm2_max, int flags, double* d_out_scores, int64_t* d_out_idx,
                          int32_t* d_stats, void* d_ws, size_t ws_bytes, t2p_stream stream);

@@ -200,3 +200,26 @@ def test_config1_topk_ids_end_to_end_independent(coarse_model):
     # the remaining queries still return the same SET up to the tied pair
     for q in np.nonzero(~comparable)[0]:
         assert len(set(idx[q].tolist()) ^ set(ref_idx[q, :10].tolist())) <= 2
+
+
+def test_pointnet_activations_beyond_fp16_fall_back_to_fp32():
+    """Weights that drive the activations past the fp16 range (gain 8 per layer: features ~1e9): the tensor-core layers flag the
+    overflow on the device and the exact-fp32 kernels redo them -- the result stays at fp32 accuracy instead of inf / NaN."""
+    from text2pos_cvpr2022_b200 import default_args
+    from text2pos_cvpr2022_b200.pointnet2 import PointNet2
+
+    pn = PointNet2(len(syn.KNOWN_CLASSES), len(syn.COLOR_NAMES), default_args(embed_dim=256))
+    syn.randomize_module_(pn, 3, gain=8.0)
+    sd = cpu_state_dict(pn)
+    pn = pn.cuda().eval()
+    packed = syn.synth_packed_cells(4, 3)
+    start = torch.zeros(packed.pos.shape[0], dtype=torch.int32)
+    off = packed.cell_offsets.tolist()
+    for a, b in zip(off[:-1], off[1:]):
+        start[a:b] = a
+    got = pn.features_packed(packed.pos.cuda(), packed.rgb.cuda(), start.cuda())
+    with torch.no_grad():
+        ref = torch.cat([oracle.pointnet.pointnet2_features(sd, "", packed.rgb[a:b], packed.pos[a:b], True) for a, b in packed.cell_slices()])
+    assert float(ref.abs().max()) > 1e6 and bool(torch.isfinite(got).all())
+    rel = float((got.cpu() - ref).abs().max() / ref.abs().max())
+    assert rel < 2e-5, rel

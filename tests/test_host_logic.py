@@ -252,3 +252,26 @@ def test_pointnet_pack_emits_tensor_core_images():
         v = w[k, n] * 256.0
         hi, lo = float(img[j, chunk, 0, nn, pu * 8 + e]), float(img[j, chunk, 1, nn, pu * 8 + e])
         assert hi == float(np.float16(v)) and abs(hi + lo - v) <= 2.0 ** -21 * abs(v) + 1e-12
+
+
+def test_weights_outside_the_fp16_range_keep_the_fp32_kernels():
+    """BatchNorm folding with a tiny running_var can push a folded weight past the fp16 range (2^8 * |w| >= 65504): such a layer
+    must not get tensor-core images (the kernels then take the exact-fp32 path) instead of silently packing inf."""
+    from text2pos_cvpr2022_b200.pointnet2 import PointNet2
+
+    pn = PointNet2(len(syn.KNOWN_CLASSES), len(syn.COLOR_NAMES), default_args(embed_dim=256))
+    syn.randomize_module_(pn, 3)
+    sd = cpu_state_dict(pn)
+    sd["sa2.point_conv.local_nn.1.1.running_var"][5] = 0.0  # 1/sqrt(eps) = 316 ...
+    sd["sa2.point_conv.local_nn.1.1.weight"][5] = 40.0       # ... times gamma: output channel 5 of SA2's second layer explodes
+    d = packing.pack_pointnet2(packing.BlobBuilder(), sd, "", True)
+    assert d.sa_l2_tc_off[1] == -1 and d.sa_l2_tc_off[2] >= 0 and d.ga_l2_tc_off >= 0
+    assert packing.fits_fp16_split(np.array([200.0]), 256.0) and not packing.fits_fp16_split(np.array([240.0]), 256.0)
+    assert not packing.fits_fp16_split(np.array([np.inf]), 1.0)
+    enc = LanguageEncoder(syn.known_words(), 256, bi_dir=True)
+    syn.randomize_module_(enc, 1)
+    sd = cpu_state_dict(enc)
+    assert packing.pack_lstm(packing.BlobBuilder(), sd, "").whh_tc_off >= 0
+    sd["lstm.weight_hh_l0"][3, 7] = 300.0
+    d = packing.pack_lstm(packing.BlobBuilder(), sd, "")
+    assert d.whh_tc_off == -1 and d.xproj4_off == -1 and d.whh_reg_off >= 0

@@ -22,6 +22,11 @@ RETRIEVE_FORCE_GENERIC = 1
 RETRIEVE_FORCE_RESCAN = 2
 
 
+def retrieve_max_ctas(n: int) -> int:
+    """``T2P_RETRIEVE_MAX_CTAS(n)`` flag bits."""
+    return (int(n) & 0xff) << 8
+
+
 class LinearDesc(C.Structure):
     _fields_ = [("w_off", C.c_int64), ("b_off", C.c_int64), ("k", C.c_int32), ("n", C.c_int32)]
 

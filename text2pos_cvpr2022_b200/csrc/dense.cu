@@ -1,5 +1,7 @@
 // Dense layers of the encoders: fused linear(+concat)(+ReLU)(+group max), row normalisation, and the
 // edge formulations of PointConv (set abstraction) and DynamicEdgeConv, all on the exact-fp32 tile GEMM.
+#include <algorithm>
+
 #include "gemm.cuh"
 #include "kernels.h"
 
@@ -22,8 +24,9 @@ struct ConcatLoader {
 template <bool GROUPMAX>
 __global__ void __launch_bounds__(GTHREADS)
 linear_kernel(ConcatLoader a, const float* __restrict__ W, const float* __restrict__ bias, int N, int relu,
-              float* __restrict__ y, int ldy, int rows_per_group) {
+              float* __restrict__ y, int ldy, int rows_per_group, const int32_t* __restrict__ run_if) {
   __shared__ GemmSmem sm;
+  if (run_if != nullptr && *run_if == 0) return;  // conditional re-run (block-uniform)
   a.row0 = blockIdx.x * GBM;
   const int n0 = blockIdx.y * GBN;
   const int K = a.Ka + a.Kb;
@@ -74,14 +77,14 @@ linear_kernel(ConcatLoader a, const float* __restrict__ W, const float* __restri
 
 static int launch_linear_impl(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
                               const float* bias, int N, bool relu, float* y, int ldy, int rows_per_group,
-                              cudaStream_t s) {
+                              cudaStream_t s, const int32_t* run_if = nullptr) {
   if (M <= 0 || N <= 0) return T2P_OK;
   ConcatLoader a{xa, xb ? xb : xa, Ka, lda, Kb, ldb, M, 0};
   dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN);
   if (rows_per_group > 0)
-    linear_kernel<true><<<grid, GTHREADS, 0, s>>>(a, W, bias, N, 1, y, ldy, rows_per_group);
+    linear_kernel<true><<<grid, GTHREADS, 0, s>>>(a, W, bias, N, 1, y, ldy, rows_per_group, run_if);
   else
-    linear_kernel<false><<<grid, GTHREADS, 0, s>>>(a, W, bias, N, relu ? 1 : 0, y, ldy, 0);
+    linear_kernel<false><<<grid, GTHREADS, 0, s>>>(a, W, bias, N, relu ? 1 : 0, y, ldy, 0, run_if);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }
@@ -95,8 +98,21 @@ int launch_linear_concat(const float* xa, int Ka, int lda, const float* xb, int 
   return launch_linear_impl(xa, Ka, lda, xb, Kb, ldb, M, W, bias, N, relu, y, ldy, 0, s);
 }
 int launch_linear_groupmax(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
-                           const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s) {
-  return launch_linear_impl(xa, Ka, lda, xb, Kb, ldb, M, W, bias, N, true, out, ldo, rows_per_group, s);
+                           const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s,
+                           const int32_t* run_if) {
+  return launch_linear_impl(xa, Ka, lda, xb, Kb, ldb, M, W, bias, N, true, out, ldo, rows_per_group, s, run_if);
+}
+
+__global__ void zero_if_kernel(float* __restrict__ p, size_t n, const int32_t* __restrict__ flag) {
+  if (*flag == 0) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+int launch_zero_if(float* p, size_t n, const int32_t* flag, cudaStream_t s) {
+  if (n == 0) return T2P_OK;
+  zero_if_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, s>>>(p, n, flag);
+  T2P_LAUNCH_CHECK();
+  return T2P_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -145,10 +161,12 @@ constexpr int SA_MAX_M = 512;
 __global__ void __launch_bounds__(GTHREADS)
 sa_edge_kernel(const float* __restrict__ T, const float* __restrict__ S, const int32_t* __restrict__ nbr,
                const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int P, int m,
-               int C1, const float* __restrict__ W2, const float* __restrict__ b2, int C2, float* __restrict__ out) {
+               int C1, const float* __restrict__ W2, const float* __restrict__ b2, int C2, float* __restrict__ out,
+               const int32_t* __restrict__ run_if) {
   __shared__ GemmSmem sm;
   __shared__ TileReduceSmem rs;
   __shared__ int incl[SA_MAX_M];
+  if (run_if != nullptr && *run_if == 0) return;  // conditional re-run (block-uniform)
   __shared__ int rowT[GBM], rowS[GBM];
   const int o = blockIdx.z, t = blockIdx.x, n0 = blockIdx.y * GBN;
   const int tid = threadIdx.x;
@@ -217,13 +235,13 @@ sa_edge_kernel(const float* __restrict__ T, const float* __restrict__ S, const i
 
 int launch_sa_edge(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt,
                    const int32_t* obj_cell_start, int quirk, int n_obj, int P, int m, int C1, const float* W2,
-                   const float* b2, int C2, float* out, cudaStream_t s) {
+                   const float* b2, int C2, float* out, cudaStream_t s, const int32_t* run_if) {
   if (n_obj <= 0) return T2P_OK;
   T2P_REQUIRE(m <= SA_MAX_M, T2P_ERR_UNSUPPORTED, "set abstraction: m=%d centres per object > %d", m, SA_MAX_M);
   T2P_REQUIRE(n_obj <= 65535, T2P_ERR_UNSUPPORTED, "set abstraction: n_obj=%d > 65535 per call (chunk the cells)", n_obj);
   const int rows_max = m * (T2P_MAX_NEIGHBORS + (quirk ? 1 : 0));
   dim3 grid((rows_max + GBM - 1) / GBM, (C2 + GBN - 1) / GBN, n_obj);
-  sa_edge_kernel<<<grid, GTHREADS, 0, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, C1, W2, b2, C2, out);
+  sa_edge_kernel<<<grid, GTHREADS, 0, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, C1, W2, b2, C2, out, run_if);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

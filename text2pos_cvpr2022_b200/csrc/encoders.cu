@@ -35,6 +35,7 @@ static int pn_dims(const t2p_pointnet2_desc* d, int P, PnDims* o) {
 struct PnWorkspace {
   int32_t *ctr_idx, *nbr, *cnt;
   float *cpos[3], *T, *S, *x[3], *gah, *f0, *f1;
+  int32_t* flags;  // [8] fp16 range flags of the tensor-core layers (SA1..3, global abstraction)
 };
 
 static size_t pn_carve(const PnDims& d, int n_obj, Arena& a, PnWorkspace* w) {
@@ -54,6 +55,7 @@ static size_t pn_carve(const PnDims& d, int n_obj, Arena& a, PnWorkspace* w) {
   w->gah = a.take<float>(n * d.Pd[3] * d.ga_h);
   w->f0 = a.take<float>(n * d.ga_o);
   w->f1 = a.take<float>(n * d.f1);
+  w->flags = a.take<int32_t>(8);
   return a.used;
 }
 
@@ -139,6 +141,7 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
   pn_carve(d, n_obj, a, &ws);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "pointnet2: workspace %zu < %zu bytes", ws_bytes, a.used);
   cudaStream_t s = as_stream(stream);
+  T2P_CUDA(cudaMemsetAsync(ws.flags, 0, 8 * sizeof(int32_t), s));  // fp16 range flags: SA1..3, global abstraction
 
   const float* x_in = d_rgb;
   const float* pos_in = d_pos;
@@ -154,8 +157,15 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
     if (desc->sa_l2_tc_off[l] >= 0 && sa_edge_tc_supported(C1, C2, m) &&
         (size_t)desc->sa_l2_tc_off[l] + (size_t)C1 * C2 <= w->n_floats) {
       // second layer + ReLU + max on the tensor cores (fp16 hi/lo split, fp32 accumulate)
+      // second layer + ReLU + max on the tensor cores (fp16 hi/lo split, fp32 accumulate).  If an activation did not fit the
+      // fp16 range the kernel raises ws.flags[l] and the two launches behind it redo the layer in exact fp32 (they return
+      // at once otherwise): results stay within the 1e-4 contract for any weights, at tensor-core speed for sane ones.
       T2P_TRY(launch_sa_edge_tc(ws.T, ws.S, ws.nbr, ws.cnt, d_obj_cell_start, desc->self_loop_quirk, n_obj, Pd, m, C1,
-                                wptr(w, desc->sa_l2_tc_off[l]), wptr(w, desc->sa_l2[l].b_off), ws.x[l], sm_count_cached(), s));
+                                wptr(w, desc->sa_l2_tc_off[l]), wptr(w, desc->sa_l2[l].b_off), ws.x[l], sm_count_cached(),
+                                ws.flags + l, s));
+      T2P_TRY(launch_zero_if(ws.x[l], (size_t)n_obj * m * C2, ws.flags + l, s));
+      T2P_TRY(launch_sa_edge(ws.T, ws.S, ws.nbr, ws.cnt, d_obj_cell_start, desc->self_loop_quirk, n_obj, Pd, m, C1,
+                             wptr(w, desc->sa_l2[l].w_off), wptr(w, desc->sa_l2[l].b_off), C2, ws.x[l], s, ws.flags + l));
     } else {
       T2P_TRY(launch_sa_edge(ws.T, ws.S, ws.nbr, ws.cnt, d_obj_cell_start, desc->self_loop_quirk, n_obj, Pd, m, C1,
                              wptr(w, desc->sa_l2[l].w_off), wptr(w, desc->sa_l2[l].b_off), C2, ws.x[l], s));
@@ -180,7 +190,10 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
   if (desc->ga_l2_tc_off >= 0 && linear_groupmax_tc_supported(d.ga_h, d.ga_o) &&
       (size_t)desc->ga_l2_tc_off + (size_t)d.ga_h * d.ga_o <= w->n_floats) {
     T2P_TRY(launch_linear_groupmax_tc(ws.gah, n_obj * m3, d.ga_h, wptr(w, desc->ga_l2_tc_off), wptr(w, desc->ga_l2.b_off), d.ga_o,
-                                      m3, ws.f0, sm_count_cached(), s));
+                                      m3, ws.f0, sm_count_cached(), ws.flags + 3, s));
+    T2P_TRY(launch_zero_if(ws.f0, (size_t)n_obj * d.ga_o, ws.flags + 3, s));
+    T2P_TRY(launch_linear_groupmax(ws.gah, d.ga_h, d.ga_h, nullptr, 0, 0, n_obj * m3, wptr(w, desc->ga_l2.w_off),
+                                   wptr(w, desc->ga_l2.b_off), d.ga_o, m3, ws.f0, d.ga_o, s, ws.flags + 3));
   } else {
     T2P_TRY(launch_linear_groupmax(ws.gah, d.ga_h, d.ga_h, nullptr, 0, 0, n_obj * m3, wptr(w, desc->ga_l2.w_off),
                                    wptr(w, desc->ga_l2.b_off), d.ga_o, m3, ws.f0, d.ga_o, s));

@@ -12,7 +12,10 @@ int launch_linear_concat(const float* xa, int Ka, int lda, const float* xb, int 
                          const float* bias, int N, bool relu, float* y, int ldy, cudaStream_t s);
 // out[row / rows_per_group, N] = max over the group's rows of relu([xa|xb] . W + bias); out must be zeroed
 int launch_linear_groupmax(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
-                           const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s);
+                           const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s,
+                           const int32_t* run_if = nullptr);
+// p[0..n) = 0 if *flag != 0 (device-side conditional, used with the `run_if` re-runs below)
+int launch_zero_if(float* p, size_t n, const int32_t* flag, cudaStream_t s);
 int launch_l2_normalize_rows(float* x, int M, int width, int ld, cudaStream_t s);
 
 // PointConv message + second local_nn layer + max aggregation for one set-abstraction level:
@@ -21,7 +24,9 @@ int launch_l2_normalize_rows(float* x, int M, int width, int ld, cudaStream_t s)
 // Edges of centre c: its ball-query list (nbr/cnt) plus, with the quirk, flat point (lo*m + c) of the cell.
 int launch_sa_edge(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt,
                    const int32_t* obj_cell_start, int quirk, int n_obj, int P, int m, int C1, const float* W2,
-                   const float* b2, int C2, float* out, cudaStream_t s);
+                   const float* b2, int C2, float* out, cudaStream_t s, const int32_t* run_if = nullptr);
+// `run_if` (device int, may be NULL): the kernel returns immediately unless *run_if != 0 -- the exact-fp32 re-run of a
+// layer whose tensor-core pass flagged an activation outside the fp16 range.
 
 // DynamicEdgeConv second layer + max over neighbours + max over the cell's objects:
 //   pooled[cell(i), :] = max_i max_{j in knn(i)} relu(relu(AB[i, :D] + AB[j, D:]) . W2 + b2)
@@ -32,10 +37,10 @@ int launch_edgeconv(const float* AB, const int32_t* knn, const int32_t* obj_cell
 bool sa_edge_tc_supported(int C1, int C2, int m);
 int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt, const int32_t* obj_cell_start,
                       int quirk, int n_obj, int P, int m, int C, const float* w_img, const float* b2, float* out, int sms,
-                      cudaStream_t s);
+                      int32_t* overflow_flag, cudaStream_t s);
 bool linear_groupmax_tc_supported(int K, int N);
 int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, const float* bias, int N, int group, float* out,
-                              int sms, cudaStream_t s);
+                              int sms, int32_t* overflow_flag, cudaStream_t s);
 int launch_fps_ball(const float* pos, int n_obj, int P, int m, float r2, int32_t* ctr_idx, float* cpos,
                     int32_t* nbr, int32_t* cnt, cudaStream_t s);
 int launch_fps_ball_mode(const float* pos, int n_obj, int P, int m, float r2, int mode, int do_ball, int32_t* ctr_idx,

@@ -5,7 +5,14 @@
 // (W*2^8 = hi + lo, relative error 2^-22): 2 x 128 TMEM columns (two fp16 per 32-bit column), written once with
 // tcgen05.st.  The A operand therefore never touches shared memory again (the SS form re-read 192 KB of weights per
 // step, ~1500 cycles of shared-memory bandwidth).  The hidden state lives in shared memory of every CTA as the UMMA B
-// operand [16 sequences x 256] fp16 hi/lo (h*2^4 = hi + lo; K-major, 128-byte swizzle), double buffered.  One step:
+// operand [16 sequences x 256] fp16 hi/lo (h*2^4 = hi + lo), double buffered, K-major in the NON-swizzled ("interleaved")
+// core-matrix layout ordered [source CTA 8][8-sequence half 2][k-unit 4][hi|lo][8 sequences x 16 bytes]: the 32 units x 16
+// sequences a CTA produces per step are then ONE contiguous 2 KB slice of every destination's buffer (the 8 units x 8
+// sequences of one epilogue warp a 256-byte block of it); the slice is staged in local shared memory and shipped with ONE
+// bulk DSMEM copy per destination (cp.async.bulk.shared::cluster.shared::cta, completing bytes on the destination's
+// mbarrier; each of the 8 warps of an epilogue set issues one) instead of 32 lanes x 4 st.async of 16 bytes per warp.  Measured on B200 (tools/dsmem_bench.cu, profiles/r02_dsmem_bench.json): the SM-to-SM
+// network sustains 21-35 B/clk per SM with bulk copies against 10-12 B/clk with st.async in this traffic pattern, and
+// the network was what bound a step.  One step:
 //   control warp : wait for h_{t-1} (mbarrier transaction count), fence.proxy.async, one elected lane issues 48
 //                  tcgen05.mma kind::f16 (M = 128 gate columns, N = 16 sequences, K = 16; products hi*hi + hi*lo +
 //                  lo*hi, fp32 accumulation in TMEM), commit to an mbarrier.  The loop runs warp-uniformly so that the
@@ -14,9 +21,10 @@
 //                  unit-major so that 4 consecutive lanes hold the gates i,f,g,o of one unit): tcgen05.ld, 4x4 block
 //                  transpose over the 4 lanes of a unit (two butterfly stages of predicated selects + shuffles; each
 //                  thread then owns one unit for 2 sequences), + input projection (per-token table, L2), cell update in
-//                  registers with MUFU-only activations, h -> fp16 hi/lo, staged through 256 bytes of shared memory
-//                  per warp into 16-byte chunks of the swizzled B layout, one st.async per chunk and peer CTA that
-//                  completes bytes on the peer's h mbarrier.
+//                  registers with MUFU-only activations, h -> fp16 hi/lo into the warp's 256-byte block of the 2 KB staging
+//                  slice (one per group and buffer parity: it is reused two steps later, when every peer has provably
+//                  consumed it), fence.proxy.async, named barrier of the set's 8 warps, then warp w ships the slice to CTA
+//                  (rank + w) % 8 with one bulk copy (an elected lane; all operands warp-uniform).
 // No cluster barrier, no __syncthreads and no fence sits on the step.  Dropping the lo*lo product and the fp16
 // rounding of lo bound the relative error of a product by ~3*2^-22: fp32-grade results (tests: 1e-4 vs the oracle).
 #include <cooperative_groups.h>
@@ -35,11 +43,15 @@ constexpr int LTC_H = 256;
 constexpr int LTC_CS = 8;        // CTAs per cluster
 constexpr int LTC_NS = 16;       // sequences per cluster (UMMA N)
 constexpr int LTC_MAXG = 4;       // ping-pong groups of <= 16 sequences per cluster
-constexpr int LTC_EPI_WARPS = 8;
-constexpr int LTC_THREADS = 32 * (LTC_EPI_WARPS + 1);  // warps 0-7: epilogue, warp 8: control
+constexpr int LTC_EPI_SETS = 2;    // epilogue warp sets: set s serves groups s, s + 2 (their latency chains overlap)
+constexpr int LTC_EPI_WARPS = 8 * LTC_EPI_SETS;
+constexpr int LTC_GPS = LTC_MAXG / LTC_EPI_SETS;       // groups per epilogue set
+constexpr int LTC_THREADS = 32 * (LTC_EPI_WARPS + 1);  // warps 0-15: epilogue, warp 16: control
 constexpr int LTC_W_HALFS = 2 * 128 * 256;      // per (direction, rank): hi|lo x 128 rows x 256 k fp16 = 128 KB
-constexpr int LTC_HB_PART = 4 * LTC_NS * 128;   // one of {hi, lo}: 4 K-chunks x 16 rows x 128 bytes = 8 KB
-constexpr int LTC_HB_BUF = 2 * LTC_HB_PART;     // hi + lo
+constexpr int LTC_HB_BUF = 16 * 1024;           // one h buffer: 16 K blocks x [k-unit 2][half 2][hi|lo][128 B] = 16 KB
+constexpr int LTC_HB_LBO = 256;                 // bytes between the two k-units (core matrices along K) of a K block
+constexpr int LTC_HB_SBO = 1024;                // bytes between the two 8-sequence halves (core matrices along N)
+constexpr int LTC_STAGE_BYTES = LTC_MAXG * 2 * 2048;  // [group][parity] 2 KB slices = [half 2][k-unit 4][hi|lo][128 B]
 constexpr int LTC_TMEM_COLS = 512;              // [0,128) W hi, [128,256) W lo, [256 + 16 g, +16) accumulator of group g
 constexpr int LTC_D_COL = 256;
 constexpr float LTC_UNSCALE = 1.f / 4096.f;     // 2^-8 (W) * 2^-4 (h)
@@ -97,10 +109,22 @@ __device__ __forceinline__ uint32_t ltc_map_rank(uint32_t local_addr, uint32_t r
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void ltc_st_async_v4(uint32_t remote_addr, uint4 v, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-               ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+// bulk DSMEM copy: `bytes` from this CTA's shared memory to a (cluster-mapped) address of a peer, completing the bytes on
+// the peer's mbarrier
+__device__ __forceinline__ void ltc_bulk_copy(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar)
                : "memory");
+}
+// K-major operand in the non-swizzled core-matrix layout: core matrix = 8 rows x 16 bytes, contiguous; LBO = byte distance
+// between the two core matrices of a K = 16 (fp16) instruction along K, SBO = between 8-row groups along N.
+__device__ __forceinline__ uint64_t ltc_desc_interleave_kmajor(uint32_t smem_addr_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr_bytes & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(LTC_HB_LBO >> 4) << 16;
+  d |= (uint64_t)(LTC_HB_SBO >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100); swizzle mode 0 = none
+  return d;
 }
 // MUFU-only activations (ex2.approx + rcp.approx, ~2 ulp each, no slow-path branches): absolute error ~2e-7
 __device__ __forceinline__ float ltc_rcp(float x) {
@@ -133,9 +157,9 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   const int NG = (ns + LTC_NS - 1) / LTC_NS;
   int nsg[LTC_MAXG], b0g[LTC_MAXG];  // sequences per group (balanced), first batch row of each group
   uint32_t step_bytes[LTC_MAXG];     // h of a group's real sequences per step: 256 units x (hi + lo) fp16 each
-  uint8_t* hb_smem = base;                                          // [NG groups][2 buffers][hi|lo][4 chunks][16 x 128 B]
-  uint8_t* stage_smem = hb_smem + (size_t)NG * 2 * LTC_HB_BUF;      // [8 warps][hi|lo][8 seqs][8 units] fp16 = 256 B each
-  LtcBars* bars = reinterpret_cast<LtcBars*>(stage_smem + LTC_EPI_WARPS * 256);
+  uint8_t* hb_smem = base;                                          // [NG groups][2 buffers][16 KB]
+  uint8_t* stage_smem = hb_smem + (size_t)NG * 2 * LTC_HB_BUF;      // [group][parity][8 warps][hi|lo][8 seqs][8 units] fp16
+  LtcBars* bars = reinterpret_cast<LtcBars*>(stage_smem + LTC_STAGE_BYTES);
   int* tok = reinterpret_cast<int*>(bars + 1);                      // [group][NS][T]
   int* len = tok + LTC_MAXG * LTC_NS * T;                           // [group][NS]
 
@@ -152,7 +176,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
       nsg[g] = g < NG ? (ns + NG - 1 - g) / NG : 0;
       b0g[g] = first;
       first += nsg[g];
-      step_bytes[g] = (uint32_t)nsg[g] * 1024u;
+      step_bytes[g] = (uint32_t)((nsg[g] + 7) / 8) * 8192u;  // 8 source CTAs x 1 KB per 8-sequence half in use
     }
   }
 
@@ -192,7 +216,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
     steps = max(steps, max_len[g]);
   }
 
-  if (warp < LTC_EPI_WARPS) {
+  if (warp < 8) {
     // W_hh slice -> tensor memory: thread = row m (TMEM lane 32*(warp%4) + lane), warps 0-3 write the hi part, 4-7 the lo
     // part; element k of the row sits in the (k%2) half of 32-bit column k/2.  Coalesced: [k-unit][row] x 16 bytes.
     const int q = warp & 3, part = warp >> 2;
@@ -229,7 +253,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
         if (step > 0) {
           mbar_wait(&bars->h_bar[g][cur], (uint32_t)(((step - 1) >> 1) & 1));
           if (lane == 0) mbar_expect_tx(&bars->h_bar[g][cur], step_bytes[g]);  // re-arm for step + 2
-          fence_proxy_async_smem();  // h arrived through the generic proxy (st.async), the UMMA reads via the async proxy
+          // no proxy fence: h arrives through the async proxy (bulk copies) and the UMMA reads through it too
         }
         tc_fence_after_sync();
         if (ltc_elect_one()) {
@@ -239,15 +263,11 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
 #pragma unroll
           for (int prod = 0; prod < 3; ++prod) {  // W_hi*h_hi, W_hi*h_lo, W_lo*h_hi
             const uint32_t a_col = tmem_base + (prod == 2 ? 128 : 0);
-            const uint32_t ha = hb + (prod == 1 ? LTC_HB_PART : 0);
+            const uint64_t b_desc = ltc_desc_interleave_kmajor(hb + (prod == 1 ? 128 : 0));
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-              const uint64_t b_desc = umma_desc_sw128_kmajor(ha + kc * (LTC_NS * 128));
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {  // K = 16 fp16 per instruction: 8 TMEM columns of A, 32 bytes of B
-                umma_f16_ts(tmem_d, a_col + (kc * 4 + ks) * 8, b_desc + 2 * ks, idesc, acc);
-                acc = true;
-              }
+            for (int kb = 0; kb < 16; ++kb) {  // K = 16 fp16 per instruction: 8 TMEM columns of A; B: source CTA kb/2, k-units 2(kb%2), +1
+              umma_f16_ts(tmem_d, a_col + kb * 8, b_desc + (uint64_t)(((kb >> 1) * 2048 + (kb & 1) * 512) >> 4), idesc, acc);
+              acc = true;
             }
           }
           umma_commit(&bars->mma_bar[g]);
@@ -256,59 +276,69 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane m = 32*q + lane  <->  unit 8*q + lane/4, gate lane%4; columns = sequences =====
-    const int q = warp & 3, hf = warp >> 2;
+    // ===== epilogue warps: TMEM lane m = 32*q + lane  <->  unit 8*q + lane/4, gate lane%4; columns = sequences.  Two sets of
+    // 8 warps: set gs serves groups gs and gs + 2.  The epilogue of a group is one long dependent chain (mbarrier wake-up,
+    // tcgen05.ld, transposes, six dependent MUFU activations, staging, proxy fence, bulk copies: ~1,500 cycles) -- with one
+    // set the chains of the four groups ran back to back and bounded the step; two sets overlap them. =====
+    const int q = warp & 3, hf = (warp >> 2) & 1, gs = warp >> 3;
     const int g4 = lane & 3, jj = lane >> 2;
     const bool gb0 = (g4 & 1) != 0, gb1 = (g4 & 2) != 0;
     const int unit = u0 + 8 * q + jj;
-    const int s0 = 8 * hf + 2 * g4;  // this thread finalises sequences s0, s0 + 1 of each group
-    int my_len[LTC_MAXG][2];
-    float c_state[LTC_MAXG][2], h_state[LTC_MAXG][2];
-    float4 xn[LTC_MAXG][2];
+    const int s0 = 8 * hf + 2 * g4;  // this thread finalises sequences s0, s0 + 1 of each of its groups
+    // this set's groups: gi -> g = gs + 2 gi (selected with static indices: the per-group arrays stay in registers)
+    int gq[LTC_GPS], g_nsg[LTC_GPS], g_b0[LTC_GPS], g_maxlen[LTC_GPS];
+#pragma unroll
+    for (int gi = 0; gi < LTC_GPS; ++gi) {
+      gq[gi] = gs + LTC_EPI_SETS * gi;
+      g_nsg[gi] = g_b0[gi] = g_maxlen[gi] = 0;
+#pragma unroll
+      for (int g = 0; g < LTC_MAXG; ++g)
+        if (g == gq[gi]) {
+          g_nsg[gi] = nsg[g];
+          g_b0[gi] = b0g[g];
+          g_maxlen[gi] = max_len[g];
+        }
+    }
+    int my_len[LTC_GPS][2];
+    float c_state[LTC_GPS][2], h_state[LTC_GPS][2];
+    float4 xn[LTC_GPS][2];
     const float4* xp_base = xproj4 + (size_t)dir * V * LTC_H + unit;
-    auto token_at = [&](int g, int e, int step) -> int {
-      const int L = my_len[g][e];
+    auto token_at = [&](int gi, int e, int step) -> int {
+      const int L = my_len[gi][e];
       if (step >= L) return 0;
-      return tok[(g * LTC_NS + s0 + e) * T + (dir ? (L - 1 - step) : step)];
+      return tok[(gq[gi] * LTC_NS + s0 + e) * T + (dir ? (L - 1 - step) : step)];
     };
 #pragma unroll
-    for (int g = 0; g < LTC_MAXG; ++g)
+    for (int gi = 0; gi < LTC_GPS; ++gi)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        my_len[g][e] = len[g * LTC_NS + s0 + e];
-        c_state[g][e] = 0.f;
-        h_state[g][e] = 0.f;
-        xn[g][e] = __ldg(xp_base + (size_t)token_at(g, e, 0) * LTC_H);
+        my_len[gi][e] = len[gq[gi] * LTC_NS + s0 + e];
+        c_state[gi][e] = 0.f;
+        h_state[gi][e] = 0.f;
+        xn[gi][e] = __ldg(xp_base + (size_t)token_at(gi, e, 0) * LTC_H);
       }
-    // staging: this warp's [hi|lo][8 seqs][8 units] fp16; lane l ships chunk (part = (l%16)/8, seq = 8*hf + l%8) to four
-    // CTAs: lanes 0-15 to rank+1..rank+4, lanes 16-31 to rank, rank+5..rank+7 (no two CTAs target the same peer at once)
-    __half* stage = reinterpret_cast<__half*>(stage_smem + warp * 256);
-    const int ship_part = (lane >> 3) & 1, ship_sl = lane & 7, ship_seq = 8 * hf + ship_sl;
-    // destination of that chunk inside a B buffer: K index k0 = u0 + 8*q, chunk k0/64, 16-byte unit (k0%64)/8 ^ (seq&7)
-    const int k0 = u0 + 8 * q;
-    const uint32_t ship_off = (uint32_t)(ship_part * LTC_HB_PART + (k0 >> 6) * (LTC_NS * 128) + ship_seq * 128 +
-                                         ((((k0 & 63) >> 3) ^ (ship_seq & 7)) << 4));
-    // cluster-mapped addresses of this lane's chunk slot (group 0, buffer 0) and of h_bar[0][0] in its four destination CTAs
-    uint32_t rdst[4], rbar[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int dst_rank = (lane < 16) ? (rank + 1 + r) : (r == 0 ? rank : rank + 4 + r);
-      rdst[r] = ltc_map_rank(smem_u32(hb_smem) + ship_off, (uint32_t)(dst_rank & (LTC_CS - 1)));
-      rbar[r] = ltc_map_rank(smem_u32(&bars->h_bar[0][0]), (uint32_t)(dst_rank & (LTC_CS - 1)));
-    }
+    // staging: this warp's [hi|lo][8 seqs][8 units] fp16 = block (half hf, k-unit q) of the CTA's 2 KB slice; warp w of the
+    // set ships the whole slice to CTA (rank + w) % 8 -- at any moment the 8 CTAs of the cluster target 8 different peers.
+    // Everything that feeds the copy is made provably warp-uniform (shuffle from lane 0): one UBLKCP, no per-lane loop.
+    const int lw = __shfl_sync(0xffffffffu, warp & 7, 0);
+    const uint32_t dst_rank = (uint32_t)((rank + lw) & (LTC_CS - 1));
+    // cluster-mapped addresses of this CTA's slice (group 0, buffer 0) and of h_bar[0][0] in the destination CTA
+    const uint32_t rdst = ltc_map_rank(smem_u32(hb_smem) + (uint32_t)rank * 2048u, dst_rank);
+    const uint32_t rbar = ltc_map_rank(smem_u32(&bars->h_bar[0][0]), dst_rank);
     const uint32_t tmem_src = tmem_base + ((uint32_t)(q * 32) << 16) + LTC_D_COL + 8 * hf;
 
     for (int step = 0; step < steps; ++step) {
       const int nxt = (step + 1) & 1;
 #pragma unroll
-      for (int g = 0; g < LTC_MAXG; ++g) {
-        if (step >= max_len[g]) continue;  // warp-uniform
+      for (int gi = 0; gi < LTC_GPS; ++gi) {
+        if (step >= g_maxlen[gi]) continue;  // warp-uniform
+        const int g = gq[gi];
         float4 xg[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) xg[e] = xn[g][e];
-        if (step + 1 < max_len[g]) {
+        for (int e = 0; e < 2; ++e) xg[e] = xn[gi][e];
+        if (step + 1 < g_maxlen[gi]) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) xn[g][e] = __ldg(xp_base + (size_t)token_at(g, e, step + 1) * LTC_H);
+          for (int e = 0; e < 2; ++e) xn[gi][e] = __ldg(xp_base + (size_t)token_at(gi, e, step + 1) * LTC_H);
         }
         mbar_wait(&bars->mma_bar[g], (uint32_t)(step & 1));
         tc_fence_after_sync();
@@ -343,39 +373,42 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
           const float pg_ = fmaf(pre_g, LTC_UNSCALE, xg[e].z);
           const float po = fmaf(pre_o, LTC_UNSCALE, xg[e].w);
           const float ig = ltc_sigmoid(pi), fg = ltc_sigmoid(pf), gg = ltc_tanh(pg_), og = ltc_sigmoid(po);
-          const float cn = fmaf(fg, c_state[g][e], ig * gg);
+          const float cn = fmaf(fg, c_state[gi][e], ig * gg);
           const float hn = og * ltc_tanh(cn);
-          const bool active = step < my_len[g][e];
-          c_state[g][e] = active ? cn : c_state[g][e];
-          h_state[g][e] = active ? hn : h_state[g][e];
+          const bool active = step < my_len[gi][e];
+          c_state[gi][e] = active ? cn : c_state[gi][e];
+          h_state[gi][e] = active ? hn : h_state[gi][e];
         }
-        if (step + 1 < max_len[g]) {
-          // h*2^4 -> fp16 hi/lo, staged as [part][seq-in-half][unit-in-warp]
+        if (step + 1 < g_maxlen[gi]) {  // warp-uniform, and uniform over the 8 warps of the set
+          // h*2^4 -> fp16 hi/lo, staged as [part][seq-in-half][unit-in-warp]; padding sequences of a half in use carry h = 0;
+          // an all-padding second half is neither staged nor shipped (it stays zero in every buffer)
+          uint8_t* slice = stage_smem + (size_t)(g * 2 + nxt) * 2048;
+          const uint32_t halves = (uint32_t)(g_nsg[gi] + 7) >> 3;
+          if ((uint32_t)hf < halves) {
+            __half* stage = reinterpret_cast<__half*>(slice + (hf * 4 + q) * 256);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float hs = h_state[g][e] * LTC_HSCALE;
-            const __half hi = __float2half_rn(hs);
-            const __half lo = __float2half_rn(hs - __half2float(hi));
-            stage[(0 * 8 + 2 * g4 + e) * 8 + jj] = hi;
-            stage[(1 * 8 + 2 * g4 + e) * 8 + jj] = lo;
+            for (int e = 0; e < 2; ++e) {
+              const float hs = h_state[gi][e] * LTC_HSCALE;
+              const __half hi = __float2half_rn(hs);
+              const __half lo = __float2half_rn(hs - __half2float(hi));
+              stage[(0 * 8 + 2 * g4 + e) * 8 + jj] = hi;
+              stage[(1 * 8 + 2 * g4 + e) * 8 + jj] = lo;
+            }
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the bulk copy (async proxy)
           }
-          __syncwarp();
-          const uint4 chunk = *reinterpret_cast<const uint4*>(stage + (ship_part * 8 + ship_sl) * 8);
-          __syncwarp();  // the staging area is rewritten by the next group / step
-          const uint32_t doff = (uint32_t)(g * 2 + nxt) * LTC_HB_BUF, boff = (uint32_t)(g * 2 + nxt) * 8u;
-          if (ship_seq < nsg[g]) {  // rows of padding sequences stay zero
-#pragma unroll
-            for (int r = 0; r < 4; ++r) ltc_st_async_v4(rdst[r] + doff, chunk, rbar[r] + boff);
-          }
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + gs) : "memory");  // the 8 warps of this set: the slice is complete
+          if (ltc_elect_one())
+            ltc_bulk_copy(rdst + (uint32_t)(g * 2 + nxt) * LTC_HB_BUF, smem_u32(slice), halves * 1024u,
+                          rbar + (uint32_t)(g * 2 + nxt) * 8u);
         }
       }
     }
 #pragma unroll
-    for (int g = 0; g < LTC_MAXG; ++g)
+    for (int gi = 0; gi < LTC_GPS; ++gi)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int b = b0g[g] + s0 + e;
-        if (s0 + e < nsg[g] && b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[g][e];
+        const int b = g_b0[gi] + s0 + e;
+        if (s0 + e < g_nsg[gi] && b < B) hfinal[((size_t)dir * B + b) * LTC_H + unit] = h_state[gi][e];
       }
   }
   tc_fence_before_sync();
@@ -386,7 +419,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
 }
 
 size_t lstm_tc_smem_bytes(int T) {
-  return (size_t)LTC_MAXG * 2 * LTC_HB_BUF + LTC_EPI_WARPS * 256 + sizeof(LtcBars) + ((size_t)LTC_MAXG * LTC_NS * T + LTC_MAXG * LTC_NS) * sizeof(int) + 64;
+  return (size_t)LTC_MAXG * 2 * LTC_HB_BUF + LTC_STAGE_BYTES + sizeof(LtcBars) + ((size_t)LTC_MAXG * LTC_NS * T + LTC_MAXG * LTC_NS) * sizeof(int) + 64;
 }
 
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,

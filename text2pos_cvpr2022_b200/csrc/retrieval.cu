@@ -289,7 +289,7 @@ size_t t2p_retrieve_topk_workspace(int B, int N, int D, int k) {
   const size_t kp = std::min(RT_MAX_KP, k + 6);
   size_t generic = align_up(G * B * kp * sizeof(float), 256) + align_up(G * B * kp * sizeof(int32_t), 256);
   size_t tc = 0;
-  for (int sms = 64; sms <= 160; sms += 4) {  // the plan depends on the SM count; size for the worst case
+  for (int sms = 1; sms <= 160; ++sms) {  // the plan depends on the SM count / the CTA cap; size for the worst case
     const TcPlan p = tc_plan(B, N, D, k, sms);
     if (p.ok) tc = std::max(tc, tc_workspace_bytes(p, B));
   }
@@ -321,7 +321,11 @@ int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int 
   T2P_REQUIRE(B > 0 && N > 0 && D > 0, T2P_ERR_INVALID, "retrieve_topk: B=%d N=%d D=%d must be positive", B, N, D);
   cudaStream_t s = as_stream(stream);
   if (!(flags & T2P_RETRIEVE_FORCE_GENERIC)) {
-    const TcPlan p = tc_plan(B, N, D, k, std::min(160, cached_sm_count()));
+    // a server with several batches in flight cares about SM-time per batch, not latency: T2P_RETRIEVE_MAX_CTAS(n) spreads the
+    // scan over at most n CTAs (each streams more DB tiles against its resident query tile; fewer key lists for the select)
+    const int cap = (flags >> 8) & 0xff;
+    const int sms = std::min(160, cached_sm_count());
+    const TcPlan p = tc_plan(B, N, D, k, cap > 0 ? std::min(cap, sms) : sms);
     if (p.ok)
       return launch_retrieve_tc(p, d_q, d_db, B, N, D, k, idx_base, d_db_norm2_max, (flags & T2P_RETRIEVE_FORCE_RESCAN) ? 1 : 0,
                                 d_out_scores, d_out_idx, d_stats, d_ws, ws_bytes, s);

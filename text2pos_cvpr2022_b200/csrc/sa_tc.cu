@@ -32,6 +32,7 @@ constexpr int SAT_EPI_WARP0 = 2 + SAT_PROD_WARPS;        // first of the 4 epilo
 constexpr int SAT_THREADS = 32 * (SAT_EPI_WARP0 + 4);
 constexpr int SAT_STAGES = 2;
 constexpr float SAT_WUNSCALE = 1.f / 256.f;
+constexpr float SAT_AMAX = 60000.f;  // activations above this do not fit fp16 (max 65504): the layer is redone in fp32
 
 struct SatRows {
   int rowT[SAT_ROWS];  // row of T (global point index) feeding edge r
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(SAT_THREADS, 1)
 sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, const int32_t* __restrict__ nbr,
                   const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int P, int m,
                   int n_obj, const uint4* __restrict__ w_img, const float* __restrict__ b2,
-                  float* __restrict__ out, int ldo) {
+                  float* __restrict__ out, int ldo, int32_t* __restrict__ overflow_flag) {
   constexpr int C = K;                           // row pitch of T / S
   constexpr int NKC = K / 64;                    // 64-wide K chunks
   constexpr int A_PART = SAT_ROWS * 128;         // one of {hi, lo} of an A chunk: 128 rows x 128 bytes
@@ -273,6 +274,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     const int cg = lane & 7, rsub = lane >> 3;
     int stage = 0;
     uint32_t ph = 0;
+    float amax = 0.f;  // largest activation converted to fp16 by this lane (range guard, see the end of this branch)
     for (int it = 0;; ++it) {
       const int buf = it & 1;
       mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
@@ -319,6 +321,8 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
                                   fmaxf(t1.x - s1.x, 0.f), fmaxf(t1.y - s1.y, 0.f), fmaxf(t1.z - s1.z, 0.f), fmaxf(t1.w - s1.w, 0.f)};
               uint32_t h[4], l[4];
 #pragma unroll
+              for (int j = 0; j < 8; ++j) amax = a[j] <= amax ? amax : a[j];  // NaN sticks (the comparison is false)
+#pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const __half2 hh = __floats2half2_rn(a[2 * j], a[2 * j + 1]);
                 const float2 back = __half22float2(hh);
@@ -342,6 +346,9 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_empty[buf]);
     }
+    // fp16 range guard: an activation beyond the fp16 range (or a NaN) makes this layer's tensor-core result unusable;
+    // the flag makes the host-enqueued exact-fp32 kernel behind this launch recompute the layer (it is a no-op otherwise)
+    if (!(amax <= SAT_AMAX) && overflow_flag) atomicOr(overflow_flag, 1);
   } else {
     // ===== epilogue: the last four warps own TMEM lane quadrants (warp & 3); 128 threads, named barrier 1 =====
     const int quad = warp & 3;
@@ -408,13 +415,13 @@ static size_t sat_smem_bytes() {
 template <int C>
 static int launch_sa_tc(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt, const int32_t* obj_cell_start,
                         int quirk, int n_obj, int P, int m, const float* w_img, const float* b2, float* out, int sms,
-                        cudaStream_t s) {
+                        int32_t* overflow_flag, cudaStream_t s) {
   const size_t smem = sat_smem_bytes<C>();
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "set abstraction (tensor cores): %zu bytes of shared memory", smem);
   T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<C, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(n_obj, sms);  // objects are dealt round-robin to persistent CTAs
   sa_edge_tc_kernel<C, C, false><<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj,
-                                                                reinterpret_cast<const uint4*>(w_img), b2, out, C);
+                                                                reinterpret_cast<const uint4*>(w_img), b2, out, C, overflow_flag);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }
@@ -423,10 +430,10 @@ bool sa_edge_tc_supported(int C1, int C2, int m) { return C1 == C2 && (C1 == 128
 
 int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt, const int32_t* obj_cell_start,
                       int quirk, int n_obj, int P, int m, int C, const float* w_img, const float* b2, float* out, int sms,
-                      cudaStream_t s) {
+                      int32_t* overflow_flag, cudaStream_t s) {
   if (n_obj <= 0) return T2P_OK;
-  if (C == 128) return launch_sa_tc<128>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, s);
-  return launch_sa_tc<256>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, s);
+  if (C == 128) return launch_sa_tc<128>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, overflow_flag, s);
+  return launch_sa_tc<256>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, overflow_flag, s);
 }
 
 // y[M / group, N] = max over groups of `group` consecutive rows of relu(x[M, 512] . W + b): the second layer of the global
@@ -435,7 +442,7 @@ int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const 
 bool linear_groupmax_tc_supported(int K, int N) { return K == 512 && N % 256 == 0 && N >= 256; }
 
 int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, const float* bias, int N, int group, float* out,
-                              int sms, cudaStream_t s) {
+                              int sms, int32_t* overflow_flag, cudaStream_t s) {
   if (M <= 0) return T2P_OK;
   T2P_REQUIRE(linear_groupmax_tc_supported(K, N) && group >= 1, T2P_ERR_UNSUPPORTED, "linear_groupmax (tensor cores): K=%d N=%d", K, N);
   const size_t smem = sat_smem_bytes<256>();
@@ -443,7 +450,7 @@ int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, 
   const int nblocks = N / 256, tiles = (M + SAT_ROWS - 1) / SAT_ROWS;
   dim3 grid(std::max(1, std::min(tiles, sms / nblocks)), nblocks);
   sa_edge_tc_kernel<512, 256, true><<<grid, SAT_THREADS, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, 0, 0, group, M,
-                                                                   reinterpret_cast<const uint4*>(w_img), bias, out, N);
+                                                                   reinterpret_cast<const uint4*>(w_img), bias, out, N, overflow_flag);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

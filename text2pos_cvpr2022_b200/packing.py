@@ -96,18 +96,29 @@ def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = Tru
     d.self_loop_quirk = 1 if self_loop_quirk else 0
     for l in range(3):
         k, n = d.sa_l2[l].k, d.sa_l2[l].n
+        d.sa_l2_tc_off[l] = -1
         if k == n and k in (128, 256):
             blob_w = np.concatenate(bb.chunks)[d.sa_l2[l].w_off: d.sa_l2[l].w_off + k * n].astype(np.float64).reshape(k, n)
-            d.sa_l2_tc_off[l] = bb.add_raw_u32(_sa_tc_images(blob_w))
-        else:
-            d.sa_l2_tc_off[l] = -1
+            if fits_fp16_split(blob_w, SA_TC_WSCALE):  # else: the exact-fp32 kernel serves this layer
+                d.sa_l2_tc_off[l] = bb.add_raw_u32(_sa_tc_images(blob_w))
     k, n = d.ga_l2.k, d.ga_l2.n
+    d.ga_l2_tc_off = -1
     if k == 512 and n % 256 == 0:
         blob_w = np.concatenate(bb.chunks)[d.ga_l2.w_off: d.ga_l2.w_off + k * n].astype(np.float64).reshape(k, n)
-        d.ga_l2_tc_off = bb.add_raw_u32(np.concatenate([_sa_tc_images(blob_w[:, j: j + 256]) for j in range(0, n, 256)]))
-    else:
-        d.ga_l2_tc_off = -1
+        if fits_fp16_split(blob_w, SA_TC_WSCALE):
+            d.ga_l2_tc_off = bb.add_raw_u32(np.concatenate([_sa_tc_images(blob_w[:, j: j + 256]) for j in range(0, n, 256)]))
     return d
+
+
+FP16_SAFE_MAX = 60000.0  # fp16 max is 65504
+
+
+def fits_fp16_split(w: np.ndarray, scale: float) -> bool:
+    """True if ``scale * w`` can be split into fp16 hi + lo images: finite and |scale * w| < 60000 (BatchNorm folding can
+    blow weights up: a tiny running_var gives factors up to ~316 * gamma).  Layers that do not fit keep their tensor-core
+    offset at -1 and run on the exact-fp32 kernels."""
+    w = np.asarray(w, dtype=np.float64)
+    return bool(np.isfinite(w).all() and (np.abs(w) * scale).max(initial=0.0) < FP16_SAFE_MAX)
 
 
 SA_TC_WSCALE = 256.0  # 2^8: keeps the fp16 "lo" halves of the weights out of the subnormal range
@@ -178,7 +189,7 @@ def pack_lstm(bb: BlobBuilder, sd, prefix: str) -> _lib.LstmDesc:
     d.xproj_off = bb.add(np.stack(xproj))
     d.whh_off = bb.add(np.stack(whh))
     d.whh_reg_off = bb.add(_lstm_register_tiling(np.stack(whh))) if H in (32, 64, 128, 256) else -1
-    if H == 256:
+    if H == 256 and fits_fp16_split(np.stack(whh), LSTM_TC_WSCALE):  # else: the register-resident fp32 kernel
         xp = np.stack(xproj)  # [2, V, 4H], columns g*H + u
         d.xproj4_off = bb.add(xp.reshape(2, V, 4, H).transpose(0, 1, 3, 2))  # [2, V, H, 4]
         d.whh_tc_off = bb.add_raw_u32(_lstm_tc_images(np.stack(whh)))

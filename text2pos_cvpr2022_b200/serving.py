@@ -87,7 +87,7 @@ class OnlineRetrievalEngine:
 
     def __init__(self, model, db: torch.Tensor, k: int = 10, max_batch: int = 64, max_tokens: int = 64,
                  idx_base: int = 0, cell_ids: Optional[Sequence[str]] = None, depth: int = 1, max_text_bytes: int = 1024,
-                 lstm_clusters: Optional[int] = None):
+                 lstm_clusters: Optional[int] = None, scan_ctas: Optional[int] = None):
         self.lib = _lib.load()
         self.model = model
         self.weights, desc = model.t2p_packed()
@@ -112,6 +112,13 @@ class OnlineRetrievalEngine:
 
             self.lstm_desc = copy.copy(self.lstm_desc)
             self.lstm_desc.max_groups = int(lstm_clusters)
+        # top-k scan CTAs: one per SM for a synchronous engine (lowest latency); a pipelined one caps them -- every CTA then
+        # streams several DB tiles against its resident query tile and the select reads fewer key lists: a fraction of the
+        # SM-time per batch (T2P_RETRIEVE_MAX_CTAS)
+        if scan_ctas is None:
+            scan_ctas = 0 if self.depth == 1 else 40
+        self.scan_ctas = max(0, min(255, int(scan_ctas)))
+        self.topk_flags = self.scan_ctas << 8
         # slot 0 runs on the caller's current stream (query / enqueue_*); further slots own a stream each
         self.slots = [_Slot(self, own_stream=(i > 0 or self.depth > 1)) for i in range(self.depth)]
         self._inflight = collections.deque()
@@ -159,7 +166,7 @@ class OnlineRetrievalEngine:
         db = self.db if db is None else db
         _lib.check(
             self.lib.t2p_retrieve_topk_ex(s.q.data_ptr(), db.data_ptr(), self.B, db.shape[0], db.shape[1], self.k,
-                                          self.idx_base, self.db_norm2_max.data_ptr(), 0, s.out_scores.data_ptr(),
+                                          self.idx_base, self.db_norm2_max.data_ptr(), self.topk_flags, s.out_scores.data_ptr(),
                                           s.out_idx.data_ptr(), self.stats.data_ptr(), s.ws_topk.data_ptr(),
                                           s.ws_topk.numel(), _lib.stream_ptr(self.device)),
             "retrieve_topk",
@@ -415,7 +422,7 @@ class ShardedOnlineRetrievalEngine:
         e, R = self.eng, self.world
         _lib.check(
             e.lib.t2p_retrieve_topk_ex(s.q_all.data_ptr(), db.data_ptr(), R * e.B, db.shape[0], db.shape[1], e.k, e.idx_base,
-                                       e.db_norm2_max.data_ptr(), 0, s.loc[0].data_ptr(), s.loc[1].data_ptr(),
+                                       e.db_norm2_max.data_ptr(), e.topk_flags, s.loc[0].data_ptr(), s.loc[1].data_ptr(),
                                        e.stats.data_ptr(), s.ws_topk.data_ptr(), s.ws_topk.numel(), _lib.stream_ptr(e.device)),
             "retrieve_topk",
         )

@@ -42,7 +42,8 @@ class CellStore:
     ``cell_offsets`` [n_cells+1] int32 (objects of a cell), ``cell_ids`` (strings), ``bbox_w`` [n_cells, 6] / ``cell_size``
     [n_cells] float64 (world frame, for the pose accuracies)."""
 
-    def __init__(self, raw_xyz, raw_rgb, obj_offsets, cell_offsets, cell_ids, bbox_w=None, cell_size=None):
+    def __init__(self, raw_xyz, raw_rgb, obj_offsets, cell_offsets, cell_ids, bbox_w=None, cell_size=None, obj_id_offset: int = 0):
+        self.obj_id_offset = int(obj_id_offset)  # global id of object 0 (a shard resamples its objects like the whole store does)
         self.raw_xyz = torch.as_tensor(raw_xyz, dtype=torch.float32).contiguous()
         self.raw_rgb = torch.as_tensor(raw_rgb, dtype=torch.float32).contiguous()
         self.obj_offsets = torch.as_tensor(obj_offsets, dtype=torch.int64).contiguous()
@@ -133,7 +134,8 @@ class CellStore:
         p0, p1 = int(oo[o0]), int(oo[o1])
         return CellStore(self.raw_xyz[p0:p1], self.raw_rgb[p0:p1], (self.obj_offsets[o0:o1 + 1] - p0),
                          (self.cell_offsets[lo:hi + 1] - o0), self.cell_ids[lo:hi],
-                         None if self.bbox_w is None else self.bbox_w[lo:hi], None if self.cell_size is None else self.cell_size[lo:hi])
+                         None if self.bbox_w is None else self.bbox_w[lo:hi], None if self.cell_size is None else self.cell_size[lo:hi],
+                         obj_id_offset=self.obj_id_offset + o0)
 
     # ---- the device data path ---------------------------------------------------------------------------------------
     def batch_object_points(self, cell_lo: int = 0, cell_hi: Optional[int] = None, seed: int = 0, P: int = NUM_POINTS,
@@ -141,7 +143,7 @@ class CellStore:
                             return_extras: bool = False):
         """Cells ``[cell_lo, cell_hi)`` -> ``PackedCells`` on the store's device (one kernel).  ``choice`` [n_obj, P] int32
         overrides the counter-based sampling; ``obj_id_base``: global id of the first object (default: its index in the
-        store).  ``return_extras``: also (centers64 [n_obj,3] float64, choice [n_obj,P] int32)."""
+        store + the store's ``obj_id_offset``, so a shard samples exactly like the whole store).  ``return_extras``: also (centers64 [n_obj,3] float64, choice [n_obj,P] int32)."""
         lib = _lib.load()
         _lib.require_cuda(self.raw_xyz, "cell store")
         cell_hi = self.num_cells if cell_hi is None else cell_hi
@@ -163,7 +165,7 @@ class CellStore:
         with torch.cuda.device(dev):
             _lib.check(
                 lib.t2p_batch_object_points(_lib.ptr(self.raw_xyz), _lib.ptr(self.raw_rgb), offs.data_ptr(), n_obj, P,
-                                            _lib.ptr(choice), int(seed) & _M64, int(o0 if obj_id_base is None else obj_id_base),
+                                            _lib.ptr(choice), int(seed) & _M64, int(self.obj_id_offset + o0 if obj_id_base is None else obj_id_base),
                                             _lib.ptr(pos), _lib.ptr(rgb), _lib.ptr(ctr), _lib.ptr(col), _lib.ptr(ctr64),
                                             _lib.ptr(ch_out), _lib.stream_ptr(dev)),
                 "batch_object_points",

@@ -369,3 +369,129 @@ def combine_replica_sums(parts: Sequence[Dict], top_k, threshs):
         s = sum(p["sums"][name] for p in parts)
         out.append({k: {t: s[i, j] / max(1, n) for j, t in enumerate(threshs)} for i, k in enumerate(ks)})
     return tuple(out)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the whole pipeline on R GPUs (BASELINE config 5)
+# ----------------------------------------------------------------------------------------------------------------
+class _DatasetView:
+    """``dataloader``-shaped view (``.dataset.all_poses / all_cells``) for the stage functions."""
+
+    def __init__(self, dataset):
+        self.dataset = dataset
+
+
+@torch.no_grad()
+def run_pipeline_distributed(coarse_model, fine_model, dataset, args, group=None, seed: int = 0, query_batch: int = 64,
+                             return_details: bool = False):
+    """Coarse -> fine evaluation of ``dataset`` (``all_cells`` / ``all_poses``) on the ranks of a ``torch.distributed`` group,
+    one rank per GPU:
+
+    1. DB build: the RAW cells are sharded like the embeddings (``CellStore.shard``) -- every rank resamples / encodes its own
+       block on the device, so the cell embeddings are born in place; no collective.
+    2. Coarse retrieval: queries are data-parallel (rank r owns a contiguous block of the poses); per batch one all-gather of
+       the query embeddings, the local top-k of all queries against the shard, one all-gather of the per-shard lists and the
+       merge (``ShardedCellDatabase.topk_dp``).
+    3. Fine stage: replicas only.  The query-independent object encodings of the (padded) cells are computed once, each rank
+       its block, and all-gathered (8 KB per cell); every rank then matches its own queries against their retrieved cells
+       (``run_fine_cached``: hint LSTM + SuperGlue gather kernel + pose head + accuracies on the device).
+    4. The hit counts are summed over the ranks (one all-reduce).
+
+    Returns ``(coarse_acc, acc_mean, acc_offset, acc_mean_conf, info)`` with the reference's accuracy dicts
+    (``{k: {thresh: acc}}``); ``info`` holds this rank's retrievals and stage timings (seconds)."""
+    import torch.distributed as dist
+
+    from .cell_store import CellStore, build_cell_database
+    from .retrieval import ShardedCellDatabase, shard_bounds
+
+    R, r = dist.get_world_size(group), dist.get_rank(group)
+    dev = coarse_model.t2p_device()
+    cells, poses = dataset.all_cells, dataset.all_poses
+    n_cells, n_q = len(cells), len(poses)
+    top_k, threshs = list(args.top_k), list(args.threshs)
+    K = max(top_k)
+    lo, hi = shard_bounds(n_cells, R)[r]
+    q_lo, q_hi = shard_bounds(n_q, R)[r]
+    per_q = shard_bounds(n_q, R)[0][1]  # queries per rank (the last rank may own fewer: its batches are padded)
+    times = {}
+
+    def tick(name, t0):
+        torch.cuda.synchronize(dev)
+        times[name] = time.perf_counter() - t0
+
+    # 1. sharded DB build ---------------------------------------------------------------------------------------------
+    t0 = time.perf_counter()
+    obj_before = sum(len(c.objects) for c in cells[:lo])
+    shard = CellStore.from_cells(cells[lo:hi]) if hi > lo else None
+    if shard is not None:
+        shard.obj_id_offset = obj_before
+        local_emb = build_cell_database(coarse_model, shard.to(dev), seed=seed)
+    else:
+        local_emb = torch.empty(0, coarse_model.embed_dim, device=dev)
+    tick("db_build_s", t0)
+
+    # 2. coarse retrieval, queries data-parallel ----------------------------------------------------------------------
+    t0 = time.perf_counter()
+    sdb = ShardedCellDatabase(local_emb, n_cells, group)
+    cell_ids = np.array([c.id for c in cells])
+    own = list(range(q_lo, q_hi))
+    retrievals = {}
+    for b0 in range(0, per_q, query_batch):
+        idx = [own[min(b0 + i, len(own) - 1)] if own else 0 for i in range(min(query_batch, per_q - b0))]  # padded with repeats
+        texts = [" ".join(create_hint_description(poses[q])) for q in idx]
+        q_enc = coarse_model.encode_text(texts)
+        top, _ = sdb.topk_dp(q_enc, K)
+        top = top.cpu().numpy()
+        for i, q in enumerate(idx):
+            if b0 + i < len(own):
+                retrievals[q] = cell_ids[top[i]]
+    tick("coarse_s", t0)
+    cells_dict = {c.id: c for c in cells}
+    coarse_sums = np.zeros((len(top_k), len(threshs)), dtype=np.int64)
+    for q in own:
+        accs = calc_sample_accuracies(poses[q], [cells_dict[c] for c in retrievals[q]], 0.5 * np.ones((K, 2)), top_k, threshs)
+        coarse_sums += np.array([[int(accs[k][t]) for t in threshs] for k in top_k])
+
+    # 3. fine stage: cache built in blocks, all-gathered; replicas over the queries --------------------------------------
+    t0 = time.perf_counter()
+    pad = int(args.pad_size)
+    D = fine_model.embed_dim
+    per_c = shard_bounds(n_cells, R)[0][1]
+    enc_blk = torch.zeros(per_c, pad, D, dtype=torch.float32, device=dev)
+    ctr_blk = torch.zeros(per_c, pad, 2, dtype=torch.float64, device=dev)
+    if hi > lo:
+        pstore = CellStore.from_cells(cells[lo:hi], pad, lambda cell: seeded_padding_factory(seed, cell.id))
+        pstore.obj_id_offset = lo * pad
+        part = FineCellCache.from_store(fine_model, pstore.to(dev), seed=seed)
+        enc_blk[: hi - lo] = part.obj_enc
+        ctr_blk[: hi - lo] = part.centers
+    enc_all = torch.empty(R * per_c, pad, D, dtype=torch.float32, device=dev)
+    ctr_all = torch.empty(R * per_c, pad, 2, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(enc_all, enc_blk, group=group)
+    dist.all_gather_into_tensor(ctr_all, ctr_blk, group=group)
+    cache = FineCellCache.__new__(FineCellCache)
+    cache.cell_index = {c.id: i for i, c in enumerate(cells)}
+    cache._finish(enc_all[:n_cells], ctr_all[:n_cells], cells, dev)
+    tick("fine_cache_s", t0)
+    t0 = time.perf_counter()
+    fine = run_fine_cached(fine_model, retrievals, _DatasetView(dataset), args, cache=cache, queries_per_call=query_batch,
+                           query_range=range(q_lo, q_hi), return_details=return_details)
+    tick("fine_s", t0)
+
+    # 4. reduce the hit counts ------------------------------------------------------------------------------------------
+    sums = fine[3]["sums"]
+    flat = np.concatenate([coarse_sums.reshape(-1), sums["mean"].reshape(-1), sums["offset"].reshape(-1), sums["mean_conf"].reshape(-1)])
+    t = torch.tensor(flat, dtype=torch.int64, device=dev)
+    dist.all_reduce(t, group=group)
+    flat = t.cpu().numpy()
+    nk, nt = len(top_k), len(threshs)
+    parts, o = [], 0
+    for ks in (top_k, top_k, top_k, [1]):
+        n = len(ks) * nt
+        a = flat[o: o + n].reshape(len(ks), nt)
+        parts.append({k: {th: a[i, j] / max(1, n_q) for j, th in enumerate(threshs)} for i, k in enumerate(ks)})
+        o += n
+    info = dict(retrievals=retrievals, times=times, query_range=(q_lo, q_hi), cell_range=(lo, hi), local_emb=local_emb)
+    if return_details:
+        info["details"] = fine[3]
+    return parts[0], parts[1], parts[2], parts[3], info

@@ -178,6 +178,13 @@ def load() -> C.CDLL:
                 f"text2pos_b200: native library {LIB_PATH} is missing; build it with "
                 "`python -m text2pos_cvpr2022_b200.build` (there is no CPU / PyTorch fallback)"
             )
+        from . import build as _build
+
+        if _build.built_hash() != _build.source_hash():
+            raise RuntimeError(
+                f"text2pos_b200: {LIB_PATH} was built from different sources than the ones in csrc/ (BUILD_STAMP mismatch); "
+                "rebuild with `python -m text2pos_cvpr2022_b200.build`"
+            )
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported

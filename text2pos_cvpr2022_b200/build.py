@@ -27,11 +27,33 @@ def _deps():
     ]
 
 
+STAMP_PATH = os.path.join(LIB_DIR, "BUILD_STAMP")
+
+
+def source_hash() -> str:
+    """sha256 over every source the library is built from (+ the compile flags): what ``BUILD_STAMP`` records next to the
+    ``.so`` and what ``_lib.load()`` checks, so a source edit can never ship with a stale binary (mtimes do not survive the
+    snapshot to the GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(ARCH_FLAGS + ["-O3", "-std=c++17"]).encode())
+    for p in sorted(_deps()):
+        if os.path.exists(p):
+            h.update(os.path.basename(p).encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def built_hash() -> str:
+    try:
+        return open(STAMP_PATH).read().strip()
+    except OSError:
+        return ""
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > t for p in _deps() if os.path.exists(p))
+    return not os.path.exists(LIB_PATH) or built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -62,6 +84,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     tmp = LIB_PATH + ".tmp"
     subprocess.check_call([NVCC, *ARCH_FLAGS, "-shared", "-o", tmp, *objs])
     os.replace(tmp, LIB_PATH)
+    with open(STAMP_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 

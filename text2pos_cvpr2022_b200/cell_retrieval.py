@@ -59,6 +59,8 @@ class CellRetrievalNetwork(PackedModule):
         from .modules import tokenize
 
         tokens, lengths = tokenize(descriptions, self.language_encoder.known_words)
+        if len(lengths) and int(lengths.min()) < 1:
+            raise ValueError("empty description (the reference's packed LSTM rejects length 0 too)")
         dev = self.t2p_device()
         tok = torch.from_numpy(tokens).pin_memory().to(dev, non_blocking=True)
         ln = torch.from_numpy(lengths).pin_memory().to(dev, non_blocking=True)

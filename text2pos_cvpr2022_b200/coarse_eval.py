@@ -58,7 +58,7 @@ def eval_epoch(model, dataloader, args, return_encodings: bool = False):
     assert len(db_cell_ids) == len(dataset.all_cells)  # :137
 
     # all-pairs scores + top-k (:134-140) on the GPU; float64 ranking, (score desc, index asc)
-    kmax = int(np.max(top_k))
+    kmax = min(int(np.max(top_k)), len(db_cell_ids))  # a DB smaller than max(top_k) returns all of its cells, like argsort[0:k]
     db = CellDatabase(cell_enc, db_cell_ids)
     sorted_indices, _ = db.topk(text_enc, kmax)
     sorted_indices = sorted_indices.cpu().numpy()

@@ -98,7 +98,7 @@ class CellDatabase:
     def topk_ids(self, queries: torch.Tensor, k: int) -> np.ndarray:
         """-> [B,k] array of cell-id strings, what ``eval_epoch`` stores in ``top_retrievals``."""
         assert self.cell_ids is not None
-        idx, _ = self.topk(queries, k)
+        idx, _ = self.topk(queries, min(int(k), len(self)))  # never index the ids with the -1 padding of a short DB
         return self.cell_ids[(idx - self.idx_base).cpu().numpy()]
 
 

@@ -125,14 +125,66 @@ class OnlineRetrievalEngine:
         self._next = 0
         self.set_db(db)
 
-    # slot 0 under the historical attribute names
-    def __getattr__(self, name):
-        if name in ("d_stage", "h_stage", "tokens", "lengths", "h_tokens", "h_lengths", "d_out", "h_out", "out_scores", "out_idx",
-                    "h_scores", "h_idx", "q", "ws_lstm", "ws_topk"):
-            return getattr(self.__dict__["slots"][0], name)
-        if name == "_graphs":
-            return self.__dict__["slots"][0].graphs
-        raise AttributeError(name)
+    # ---- slot 0 (the synchronous `query` path) by name ---------------------------------------------------------------
+    @property
+    def d_stage(self):
+        return self.slots[0].d_stage
+
+    @property
+    def h_stage(self):
+        return self.slots[0].h_stage
+
+    @property
+    def tokens(self):
+        return self.slots[0].tokens
+
+    @property
+    def lengths(self):
+        return self.slots[0].lengths
+
+    @property
+    def h_tokens(self):
+        return self.slots[0].h_tokens
+
+    @property
+    def h_lengths(self):
+        return self.slots[0].h_lengths
+
+    @property
+    def d_out(self):
+        return self.slots[0].d_out
+
+    @property
+    def h_out(self):
+        return self.slots[0].h_out
+
+    @property
+    def out_scores(self):
+        return self.slots[0].out_scores
+
+    @property
+    def out_idx(self):
+        return self.slots[0].out_idx
+
+    @property
+    def h_scores(self):
+        return self.slots[0].h_scores
+
+    @property
+    def h_idx(self):
+        return self.slots[0].h_idx
+
+    @property
+    def q(self):
+        return self.slots[0].q
+
+    @property
+    def ws_lstm(self):
+        return self.slots[0].ws_lstm
+
+    @property
+    def ws_topk(self):
+        return self.slots[0].ws_topk
 
     def set_db(self, db: torch.Tensor):
         from .retrieval import db_row_norm2_max

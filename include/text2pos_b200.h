@@ -286,10 +286,19 @@ typedef struct {
   int32_t sinkhorn_iters;
   float bin_score;
   float match_threshold;
+  int64_t tc_w_off; /* D == 128 only, else -1: fp16 hi/lo images of 2^8 * W for the tensor-core kernel (csrc/superglue_tc.cu), one
+                       32 KB stage [hi|lo][128 output channels][64 fp16 of one K chunk, 16-byte units XOR-swizzled by (n & 7)]
+                       after the other in consumption order: per layer q', k', v' (columns in head-major order), merge' (rows in
+                       head-major order) 2 stages each; mlp0 (K = N = 256) 8 stages: column blocks 0,1 x K chunks 0,1 then column
+                       blocks 0,1 x K chunks 2,3; mlp3 4 stages; after the last layer final_proj 2 stages */
+  int64_t tc_b_off; /* fp32 biases for it: per layer [bq' 128 | bk' 128 | bv' 128 | bmerge 128 | b0 256 | b3 128], then bfinal 128 */
 } t2p_superglue_desc;
 
 size_t t2p_superglue_workspace(int B, int M, int N, int D);
-/* d_desc0 [B,M,D], d_desc1 [B,N,D] row layout (= reference desc.transpose(1,2)); outputs: d_P [B,M+1,N+1]
+/* With D == 128, M, N <= 32, tc_w_off >= 0 and a workspace (t2p_superglue_workspace bytes) the head runs on the tcgen05 tensor
+ * cores, floor(128 / (M + N)) samples per CTA; otherwise (or if an activation leaves the fp16 range: device-side flag) on the
+ * exact-fp32 CUDA-core kernel, one CTA per sample.
+ * d_desc0 [B,M,D], d_desc1 [B,N,D] row layout (= reference desc.transpose(1,2)); outputs: d_P [B,M+1,N+1]
  * (exp of the log assignment), d_matches0 [B,M] / d_matches1 [B,N] int64 (-1 = unmatched),
  * d_mscores0 [B,M], d_mscores1 [B,N]; optional d_dbg_scores [B,M,N] (pre-Sinkhorn scores). */
 int t2p_superglue_forward(const t2p_weights* w, const t2p_superglue_desc* desc, const float* d_desc0,

@@ -275,3 +275,52 @@ def test_weights_outside_the_fp16_range_keep_the_fp32_kernels():
     sd["lstm.weight_hh_l0"][3, 7] = 300.0
     d = packing.pack_lstm(packing.BlobBuilder(), sd, "")
     assert d.whh_tc_off == -1 and d.xproj4_off == -1 and d.whh_reg_off >= 0
+
+
+def test_superglue_tensor_core_stream_layout():
+    """pack_superglue (D = 128): the weight stream of superglue_tc_kernel holds 20 stages per layer + 2 in consumption order;
+    q'/k'/v' columns and merge' rows are in head-major order (new channel h*32 + d = reference channel 4 d + h)."""
+    from text2pos_cvpr2022_b200.superglue import SuperGlue
+
+    sg = SuperGlue({"descriptor_dim": 128, "GNN_layers": ["self", "cross"], "sinkhorn_iterations": 5})
+    syn.randomize_module_(sg, 4, gain=0.5)
+    sd = cpu_state_dict(sg)
+    bb = packing.BlobBuilder()
+    d = packing.pack_superglue(bb, sd, "", ["self", "cross"], 5, 0.2)
+    blob = bb.finish().numpy()
+    assert d.tc_w_off >= 0 and d.tc_b_off >= 0
+    n_stages = 2 * 20 + 2
+    st = blob[d.tc_w_off: d.tc_w_off + n_stages * 8192].view(np.uint32).view(np.float16).reshape(n_stages, 2, 128, 64)
+    perm = np.array([4 * dd + h for h in range(4) for dd in range(32)])
+
+    def folded(lin):
+        return blob[lin.w_off: lin.w_off + lin.k * lin.n].astype(np.float64).reshape(lin.k, lin.n)
+
+    def elem(stage, n, kk):  # value of (output channel n, k = kk within the 64-wide chunk) of a stage
+        u, e = kk // 8, kk % 8
+        pu = u ^ (n & 7)
+        return float(st[stage, 0, n, pu * 8 + e]) + float(st[stage, 1, n, pu * 8 + e])
+
+    L = 1
+    base = L * 20
+    wq, wm, w0, w3 = folded(d.q[L]), folded(d.merge[L]), folded(d.mlp0[L]), folded(d.mlp3[L])
+    for n, k in [(0, 0), (5, 7), (127, 127), (33, 64), (100, 90)]:
+        assert abs(elem(base + 0 + k // 64, n, k % 64) - 256.0 * wq[k, perm[n]]) < 1e-3 * abs(256.0 * wq[k, perm[n]]) + 1e-6
+        assert abs(elem(base + 6 + k // 64, n, k % 64) - 256.0 * wm[perm[k], n]) < 1e-3 * abs(256.0 * wm[perm[k], n]) + 1e-6
+    # mlp0: stages 8..15 = (nb0: kc0, kc1), (nb1: kc0, kc1), (nb0: kc2, kc3), (nb1: kc2, kc3)
+    order = [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (0, 3), (1, 2), (1, 3)]
+    for i, (nb, kc) in enumerate(order):
+        n, kk = 17, 9
+        want = 256.0 * w0[kc * 64 + kk, nb * 128 + n]
+        assert abs(elem(base + 8 + i, n, kk) - want) < 1e-3 * abs(want) + 1e-6
+    for kc in range(4):
+        want = 256.0 * w3[kc * 64 + 3, 77]
+        assert abs(elem(base + 16 + kc, 77, 3) - want) < 1e-3 * abs(want) + 1e-6
+    bias = blob[d.tc_b_off: d.tc_b_off + 2 * 896 + 128]
+    bq = blob[d.q[L].b_off: d.q[L].b_off + 128]
+    np.testing.assert_array_equal(bias[L * 896: L * 896 + 128], bq[perm])
+    np.testing.assert_array_equal(bias[2 * 896:], blob[d.final_proj.b_off: d.final_proj.b_off + 128])
+    # D != 128: no tensor-core stream
+    sg64 = SuperGlue({"descriptor_dim": 64, "GNN_layers": ["self"], "sinkhorn_iterations": 5})
+    d64 = packing.pack_superglue(packing.BlobBuilder(), cpu_state_dict(sg64), "", ["self"], 5, 0.2)
+    assert d64.tc_w_off == -1 and d64.tc_b_off == -1

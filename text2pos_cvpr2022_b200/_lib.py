@@ -97,6 +97,8 @@ class SuperGlueDesc(C.Structure):
         ("sinkhorn_iters", C.c_int32),
         ("bin_score", C.c_float),
         ("match_threshold", C.c_float),
+        ("tc_w_off", C.c_int64),
+        ("tc_b_off", C.c_int64),
     ]
 
 

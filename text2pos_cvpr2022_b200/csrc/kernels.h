@@ -63,6 +63,13 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
                        void* d_ws, size_t ws_bytes, cudaStream_t s);
 
 
+// SuperGlue head on the tensor cores (D = 128), csrc/superglue_tc.cu
+bool superglue_tc_supported(const t2p_superglue_desc* desc, int M, int N);
+int launch_superglue_tc(const float* blob, const t2p_superglue_desc* desc, const float* d_desc0, const int64_t* d_idx0,
+                        const float* d_desc1, const int64_t* d_idx1, int B, int M, int N, float* d_P, int64_t* d_matches0,
+                        int64_t* d_matches1, float* d_mscores0, float* d_mscores1, float* d_dbg_scores, int32_t* overflow_flag,
+                        cudaStream_t s);
+
 // tensor-core LSTM recurrence (H = 256), csrc/lstm_tc.cu
 int launch_lstm_tc(const float* xproj4, const float* w_img, const int32_t* tokens, const int32_t* lengths, int B, int T, int V,
                    float* hfinal, int max_groups, cudaStream_t s);

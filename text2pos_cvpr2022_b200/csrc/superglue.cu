@@ -76,8 +76,10 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
 superglue_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_superglue_desc d,
                  const float* __restrict__ desc0, const float* __restrict__ desc1, const int64_t* __restrict__ idx0,
                  const int64_t* __restrict__ idx1, int M, int N, int RP, float* __restrict__ outP, int64_t* __restrict__ matches0, int64_t* __restrict__ matches1,
-                 float* __restrict__ mscores0, float* __restrict__ mscores1, float* __restrict__ dbg_scores) {
+                 float* __restrict__ mscores0, float* __restrict__ mscores1, float* __restrict__ dbg_scores,
+                 const int32_t* __restrict__ run_if) {
   extern __shared__ __align__(16) float sg_smem[];
+  if (run_if != nullptr && *run_if == 0) return;  // conditional re-run behind the tensor-core kernel (block-uniform)
   const int D = d.dim, R = M + N, dh = D / SG_HEADS;
   const int tid = threadIdx.x, b = blockIdx.x;
   const int maxn = max(M, N);
@@ -280,7 +282,7 @@ extern "C" {
 
 size_t t2p_superglue_workspace(int B, int M, int N, int D) {
   (void)B; (void)M; (void)N; (void)D;
-  return 0;  // everything lives in shared memory; the descriptor travels as a kernel parameter
+  return 256;  // the fp16 range flag of the tensor-core kernel; everything else lives in shared / tensor memory
 }
 
 int t2p_superglue_forward(const t2p_weights* w, const t2p_superglue_desc* desc, const float* d_desc0, const float* d_desc1,
@@ -315,11 +317,21 @@ int t2p_superglue_forward_gather(const t2p_weights* w, const t2p_superglue_desc*
   const int RP = (M + N + SG_RT - 1) / SG_RT * SG_RT;
   const size_t smem = sg_smem_bytes(M, N, D, RP);
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "superglue: M=%d N=%d D=%d need %zu bytes of shared memory", M, N, D, smem);
-  (void)d_ws; (void)ws_bytes;
   cudaStream_t s = as_stream(stream);
+  // tensor-core path (D = 128, <= 32 rows per side, tensor-core weight images present, workspace for the range flag): several
+  // samples per CTA on tcgen05; the exact-fp32 kernel below then only runs if an activation left the fp16 range
+  const int32_t* run_if = nullptr;
+  if (superglue_tc_supported(desc, M, N) && d_ws != nullptr && ws_bytes >= sizeof(int32_t) &&
+      (size_t)desc->tc_w_off + ((size_t)desc->num_gnn_layers * 20 + 2) * 8192 <= w->n_floats) {
+    int32_t* flag = static_cast<int32_t*>(d_ws);
+    T2P_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
+    T2P_TRY(launch_superglue_tc(w->d_blob, desc, d_desc0, d_idx0, d_desc1, d_idx1, B, M, N, d_P, d_matches0, d_matches1, d_mscores0,
+                                d_mscores1, d_dbg_scores, flag, s));
+    run_if = flag;
+  }
   T2P_CUDA(cudaFuncSetAttribute(superglue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   superglue_kernel<<<B, SG_THREADS, smem, s>>>(w->d_blob, *desc, d_desc0, d_desc1, d_idx0, d_idx1, M, N, RP, d_P, d_matches0, d_matches1,
-                                               d_mscores0, d_mscores1, d_dbg_scores);
+                                               d_mscores0, d_mscores1, d_dbg_scores, run_if);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

@@ -267,4 +267,57 @@ def pack_superglue(bb: BlobBuilder, sd, prefix: str, layer_names, sinkhorn_iters
     d.sinkhorn_iters = int(sinkhorn_iters)
     d.bin_score = float(sd[prefix + "bin_score"])
     d.match_threshold = float(match_threshold)
+    d.tc_w_off, d.tc_b_off = _pack_superglue_tc(bb, d, n_layers)
     return d
+
+
+SG_TC_WSCALE = 256.0
+
+
+def _pack_superglue_tc(bb: BlobBuilder, d: "_lib.SuperGlueDesc", n_layers: int):
+    """Tensor-core weight stream + bias block of ``superglue_tc_kernel`` (csrc/superglue_tc.cu) from the BN-folded [K, N]
+    matrices already in the blob; (-1, -1) unless D == 128 and every matrix fits the fp16 hi/lo split."""
+    D = d.dim
+    if D != 128:
+        return -1, -1
+    blob = np.concatenate(bb.chunks)
+
+    def mat(lin):
+        w = blob[lin.w_off: lin.w_off + lin.k * lin.n].astype(np.float64).reshape(lin.k, lin.n)
+        return w, blob[lin.b_off: lin.b_off + lin.n].astype(np.float64)
+
+    # head-major channel order: new channel h*32 + dd = reference channel 4*dd + h (models/superglue.py:110-113 views the
+    # projection as [B, D/4, 4 heads, n]: the head index is the FAST part of the channel index)
+    perm = np.array([4 * dd + h for h in range(4) for dd in range(D // 4)])
+    words, biases = [], []
+
+    def stages(w_kn):
+        """[K, 128] -> list of K/64 stages (uint32 words of [hi|lo][128 rows][128 bytes])"""
+        img = _sa_tc_images(w_kn)  # [K/64][hi|lo][N][64 fp16] flattened, SA_TC_WSCALE = 2^8
+        return list(img.reshape(w_kn.shape[0] // 64, -1))
+
+    mats = []
+    for L in range(n_layers):
+        wq, bq = mat(d.q[L])
+        wk, bk = mat(d.k[L])
+        wv, bv = mat(d.v[L])
+        wm, bm = mat(d.merge[L])
+        w0, b0 = mat(d.mlp0[L])
+        w3, b3 = mat(d.mlp3[L])
+        mats += [wq, wk, wv, wm, w0, w3]
+        for w in (wq[:, perm], wk[:, perm], wv[:, perm], wm[perm, :]):
+            words += stages(w)
+        blocks = [stages(w0[:, j * 128:(j + 1) * 128]) for j in range(2)]  # [column block][K chunk 0..3]
+        for kpair in ((0, 1), (2, 3)):
+            for nb in range(2):
+                words += [blocks[nb][kc] for kc in kpair]
+        words += stages(w3)
+        biases += [bq[perm], bk[perm], bv[perm], bm, b0, b3]
+    wf, bf = mat(d.final_proj)
+    mats.append(wf)
+    words += stages(wf)
+    biases.append(bf)
+    if not all(fits_fp16_split(w, SG_TC_WSCALE) for w in mats):
+        return -1, -1
+    assert SG_TC_WSCALE == SA_TC_WSCALE and len(words) == n_layers * 20 + 2 and all(x.size == 8192 for x in words)
+    return bb.add_raw_u32(np.concatenate(words)), bb.add(np.concatenate(biases))

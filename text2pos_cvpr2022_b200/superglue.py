@@ -112,9 +112,11 @@ def superglue_forward(weights, desc, desc0, desc1, owner: PackedModule, return_s
     s1 = torch.empty(B, N, dtype=torch.float32, device=dev)
     sc = torch.empty(B, M, N, dtype=torch.float32, device=dev) if return_scores else None
     with torch.cuda.device(dev):
+        ws = owner.t2p_workspace(lib.t2p_superglue_workspace(B, M, N, D), dev)
         _lib.check(
             lib.t2p_superglue_forward(weights.handle, desc, _lib.ptr(desc0), _lib.ptr(desc1), B, M, N, _lib.ptr(P), _lib.ptr(m0),
-                                      _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(sc), None, 0, _lib.stream_ptr(dev)),
+                                      _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(sc), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr(dev)),
             "superglue_forward",
         )
     out = {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1, "P": P}

@@ -172,9 +172,10 @@ class SuperGlueMatch(PackedModule):
         conf = torch.empty(B, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
+            ws = self.t2p_workspace(lib.t2p_superglue_workspace(B, M, N, D), dev)
             _lib.check(lib.t2p_superglue_forward_gather(weights.handle, desc["superglue"], _lib.ptr(cache.obj_enc), _lib.ptr(idx0),
                                                         _lib.ptr(hint_enc), _lib.ptr(idx1), B, M, N, _lib.ptr(P), _lib.ptr(m0),
-                                                        _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), None, None, 0, st),
+                                                        _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), None, _lib.ptr(ws), ws.numel(), st),
                        "superglue_forward_gather")
             _lib.check(lib.t2p_linear(weights.handle, desc["off1"], _lib.ptr(hint_enc), Q * N, D, 1, _lib.ptr(hid), hid.shape[1], st), "linear")
             _lib.check(lib.t2p_linear(weights.handle, desc["off2"], _lib.ptr(hid), Q * N, hid.shape[1], 0, _lib.ptr(off), 2, st), "linear")

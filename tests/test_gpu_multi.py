@@ -118,7 +118,9 @@ def _pipeline_worker(rank, world, port, q_out, one_gpu):
         coarse, fine = coarse.eval().to(dev), fine.to(dev)
         c_acc, a_mean, a_off, a_conf, info = pe.run_pipeline_distributed(coarse, fine, ds, args, query_batch=3, return_details=True)
         # the same evaluation in ONE process (whole DB, all queries)
-        retr, c_ref = pe.run_coarse(coarse, loader, args)
+        from text2pos_cvpr2022_b200.coarse_eval import eval_epoch_store
+
+        retr, c_ref = pe.run_coarse(coarse, loader, args, eval_epoch_fn=eval_epoch_store)  # DB side on the device data path, seed 0
         store = CellStore.from_cells(ds.all_cells, args.pad_size, lambda cell: pe.seeded_padding_factory(0, cell.id)).to(dev)
         ref = pe.run_fine_cached(fine, retr, loader, args, cache=pe.FineCellCache.from_store(fine, store), return_details=True)
         flat = lambda a: [[float(a[k][t]) for t in sorted(a[k])] for k in sorted(a)]

@@ -25,7 +25,20 @@ def _collate(items: List[dict]) -> Dict[str, list]:
 
 
 @torch.no_grad()
-def eval_epoch(model, dataloader, args, return_encodings: bool = False):
+def eval_epoch_store(model, dataloader, args, return_encodings: bool = False, seed: int = 0):
+    """``eval_epoch`` with the database side on the device data path: the raw cells go into a ``CellStore`` once and
+    ``t2p_batch_object_points`` resamples / normalises them on the GPU (counter-based indices, ``seed``) instead of the
+    per-object host transforms of the cell dataset.  Same return values."""
+    from .cell_store import CellStore, build_cell_database
+
+    dataset = dataloader.dataset
+    store = CellStore.from_cells(dataset.all_cells).to(model.t2p_device())
+    cell_enc = build_cell_database(model, store, seed=seed)
+    return eval_epoch(model, dataloader, args, return_encodings, _cell_enc=(cell_enc, [c.id for c in dataset.all_cells]))
+
+
+@torch.no_grad()
+def eval_epoch(model, dataloader, args, return_encodings: bool = False, _cell_enc=None):
     assert getattr(args, "ranking_loss", "pairwise") != "triplet"  # training/coarse.py:81
     model.eval()
     top_k = list(args.top_k)
@@ -47,13 +60,16 @@ def eval_epoch(model, dataloader, args, return_encodings: bool = False):
     query_cell_ids = np.array(query_cell_ids, dtype="<U32")
 
     # database side (:121-131)
-    cell_enc, db_cell_ids = [], []
-    bs = int(args.batch_size)
-    for i0 in range(0, len(cells_dataset), bs):
-        batch = _collate([cells_dataset[i] for i in range(i0, min(i0 + bs, len(cells_dataset)))])
-        cell_enc.append(model.encode_objects(batch["objects"], batch["object_points"]))
-        db_cell_ids.extend(batch["cell_ids"])
-    cell_enc = torch.cat(cell_enc)
+    if _cell_enc is not None:  # encoded by the caller (eval_epoch_store)
+        cell_enc, db_cell_ids = _cell_enc
+    else:
+        cell_enc, db_cell_ids = [], []
+        bs = int(args.batch_size)
+        for i0 in range(0, len(cells_dataset), bs):
+            batch = _collate([cells_dataset[i] for i in range(i0, min(i0 + bs, len(cells_dataset)))])
+            cell_enc.append(model.encode_objects(batch["objects"], batch["object_points"]))
+            db_cell_ids.extend(batch["cell_ids"])
+        cell_enc = torch.cat(cell_enc)
     db_cell_ids = np.array(db_cell_ids, dtype="<U32")
     assert len(db_cell_ids) == len(dataset.all_cells)  # :137
 

@@ -309,8 +309,11 @@ struct SelParams {
 __global__ void __launch_bounds__(SEL_THREADS, 3)
 retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, const SelParams p,
                        const uint32_t* __restrict__ part_keys, const float* __restrict__ db_norm2_max,
-                       double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats) {
+                       double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats,
+                       const int32_t* __restrict__ only_flagged) {
   extern __shared__ __align__(16) uint8_t sel_raw[];
+  // second stage behind retrieve_select_warp_kernel: only the queries it could not certify are (re)done here
+  if (only_flagged != nullptr && only_flagged[blockIdx.x] == 0) return;
   SelSmem* sm = reinterpret_cast<SelSmem*>(sel_raw);
   float* qs = reinterpret_cast<float*>(sel_raw + sizeof(SelSmem));  // [D]
   uint32_t* keys = reinterpret_cast<uint32_t*>(qs + p.D);             // [nsrc*KP]
@@ -628,6 +631,177 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
   }
 }
 
+// ---- select, one WARP per query ------------------------------------------------------------------------------------------
+// The per-query work of the select is tiny (a few hundred keys, <= 32 rows to re-score); a 256-thread CTA per query spends
+// its time in barriers and occupies an SM slot for ~17 us.  Here a warp does a whole query: the sorted key lists of the scan
+// CTAs go to the warp's slice of shared memory, lane l owns lists l, l + 32, ..., and the best keys are popped one per round
+// (redux over the lanes' best heads); the first 16 candidates are re-scored in float64 (all row loads of 8 candidates in
+// flight), ranked with shuffles and CERTIFIED against the best remaining key exactly like retrieve_select_kernel; if that
+// fails the next 16 are added; a query that still cannot be certified is flagged for the CTA-per-query kernel (which also
+// owns the exact rescan).  8 queries per CTA: 64 queries occupy 8 SM slots for a few microseconds instead of 64 for 17.
+constexpr int SELW_WARPS = 8;
+constexpr int SELW_MAX_LPL = 10;  // lists per lane: nsrc <= 320
+
+__global__ void __launch_bounds__(32 * SELW_WARPS)
+retrieve_select_warp_kernel(const float* __restrict__ q, const float* __restrict__ db, const SelParams p,
+                            const uint32_t* __restrict__ part_keys, const float* __restrict__ db_norm2_max,
+                            double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats,
+                            int32_t* __restrict__ flagged) {
+  extern __shared__ __align__(16) uint8_t selw_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * SELW_WARPS + warp;
+  if (qi >= p.B) return;
+  const int D = p.D, KP = p.KP, k = p.k, nsrc = p.nsrc;
+  const int total = nsrc * KP;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(selw_raw) + (size_t)warp * total;  // [nsrc][KP], each list sorted descending
+  const uint32_t low_mask = (1u << p.nb_bits) - 1u;
+  const double NINF = __longlong_as_double(0xfff0000000000000LL);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(part_keys + (size_t)qi * total);
+    uint4* dst = reinterpret_cast<uint4*>(keys);
+    for (int t = lane; t < total / 4; t += 32) dst[t] = __ldg(src + t);
+  }
+  // the query in registers (D % 128 == 0, D <= 256 on this path) and |q|^2
+  const int nv = D >> 7;
+  float4 qv[2];
+  double qq = 0.0;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    qv[c] = c < nv ? __ldg(reinterpret_cast<const float4*>(q + (size_t)qi * D) + lane + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    qq = fma((double)qv[c].x, (double)qv[c].x, qq);
+    qq = fma((double)qv[c].y, (double)qv[c].y, qq);
+    qq = fma((double)qv[c].z, (double)qv[c].z, qq);
+    qq = fma((double)qv[c].w, (double)qv[c].w, qq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  __syncwarp();
+
+  // a full list may hide rows with keys up to its last entry
+  uint32_t m_last = 0u;
+  for (int l = lane; l < nsrc; l += 32) m_last = max(m_last, keys[l * KP + KP - 1]);
+  m_last = __reduce_max_sync(0xffffffffu, m_last);
+
+  // cursors of this lane's lists, 5 bits each (0..KP <= 32 needs 6 bits for KP = 32: use 6)
+  unsigned long long cur = 0ull;
+  auto best_of_lane = [&](uint32_t& bkey, int& bpos) {
+    bkey = 0u;
+    bpos = 0;
+#pragma unroll
+    for (int i = 0; i < SELW_MAX_LPL; ++i) {
+      const int l = lane + 32 * i;
+      const int c = (int)((cur >> (6 * i)) & 63ull);
+      if (l < nsrc && c < KP) {
+        const uint32_t x = keys[l * KP + c];
+        if (x > bkey) { bkey = x; bpos = l * KP + c; }
+      }
+    }
+  };
+  uint32_t bkey;
+  int bpos;
+  best_of_lane(bkey, bpos);
+
+  auto row_of = [&](int pos, uint32_t key) -> int {
+    const int src = pos / KP;
+    const int cta = p.dup ? (src >> 1) : src;
+    const uint32_t local = low_mask - (key & low_mask);
+    return (cta + (int)(local >> 7) * p.G) * p.tile_n + (int)(local & 127u);
+  };
+
+  // candidate r lives in lane r
+  uint32_t my_key = 0u;
+  int my_row = 0;
+  double my_score = NINF;
+  int n_cand = 0;
+  bool certified = false;
+  double tk = NINF;
+  int my_rank = 64;
+  for (int round = 0; round < 2 && !certified; ++round) {
+    // ---- pop the next 16 best keys ----
+    const int first = n_cand;
+    for (int r = first; r < first + 16; ++r) {
+      const uint32_t m = __reduce_max_sync(0xffffffffu, bkey);
+      if (m == 0u) break;  // warp-uniform: nothing left
+      const unsigned who = __ballot_sync(0xffffffffu, bkey == m);
+      const int winner = __ffs(who) - 1;
+      const int wpos = __shfl_sync(0xffffffffu, bpos, winner);
+      if (lane == r) {
+        my_key = m;
+        my_row = row_of(wpos, m);
+      }
+      if (lane == winner) {
+        const int i = (wpos / KP - lane) >> 5;
+        cur += 1ull << (6 * i);
+        best_of_lane(bkey, bpos);
+      }
+      n_cand = r + 1;
+    }
+    if (n_cand == first) break;
+    // ---- float64 re-scoring of candidates [first, n_cand): 8 at a time, all row loads in flight ----
+    for (int g0 = first; g0 < n_cand; g0 += 8) {
+      float4 v[8][2];
+#pragma unroll
+      for (int jx = 0; jx < 8; ++jx) {
+        const int f = g0 + jx;
+        const int row = __shfl_sync(0xffffffffu, my_row, f & 31);
+        const float4* rp = reinterpret_cast<const float4*>(db + (size_t)(f < n_cand ? row : 0) * D);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) v[jx][c] = (f < n_cand && c < nv) ? __ldg(rp + lane + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int jx = 0; jx < 8; ++jx) {
+        const int f = g0 + jx;
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          a = fma((double)qv[c].x, (double)v[jx][c].x, a);
+          a = fma((double)qv[c].y, (double)v[jx][c].y, a);
+          a = fma((double)qv[c].z, (double)v[jx][c].z, a);
+          a = fma((double)qv[c].w, (double)v[jx][c].w, a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (f < n_cand && lane == f) my_score = a;
+      }
+    }
+    // ---- rank by (score desc, row asc) ----
+    int r = 0;
+    for (int g = 0; g < n_cand; ++g) {
+      const double gs = __shfl_sync(0xffffffffu, my_score, g);
+      const int gr = __shfl_sync(0xffffffffu, my_row, g);
+      r += (gs > my_score || (gs == my_score && gr < my_row)) ? 1 : 0;
+    }
+    my_rank = lane < n_cand ? r : 64;
+    const unsigned kth = __ballot_sync(0xffffffffu, my_rank == k - 1);
+    tk = kth ? __shfl_sync(0xffffffffu, my_score, __ffs(kth) - 1) : NINF;
+    // ---- certification (same bound as retrieve_select_kernel) ----
+    const uint32_t ukey = max(__reduce_max_sync(0xffffffffu, bkey), m_last);
+    if (ukey == 0u) {
+      certified = true;  // every row of the DB is a candidate
+    } else if (n_cand >= k) {
+      const double bound = (double)key_upper_score(ukey, low_mask) +
+                           TC_EPS * sqrt(qq) * sqrt((double)__ldg(db_norm2_max) * (1.0 + 1e-5));
+      certified = tk > bound;
+    }
+  }
+  if (certified) {
+    if (my_rank < k) {
+      out_s[(size_t)qi * k + my_rank] = my_score;
+      out_i[(size_t)qi * k + my_rank] = p.idx_base + (int64_t)my_row;
+    }
+    for (int r = n_cand + lane; r < k; r += 32) {  // N < k: pad
+      out_s[(size_t)qi * k + r] = NINF;
+      out_i[(size_t)qi * k + r] = -1;
+    }
+    if (lane == 0) {
+      flagged[qi] = 0;
+      if (stats) atomicAdd(stats + 0, 1);
+    }
+  } else if (lane == 0) {
+    flagged[qi] = 1;  // the CTA-per-query kernel redoes this query (wider candidate set, exact rescan if needed)
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -712,7 +886,7 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
 }
 
 size_t tc_workspace_bytes(const TcPlan& p, int B) {
-  return align_up((size_t)B * p.nsrc * p.KP * sizeof(uint32_t), 256) + 256 /* norm bound */;
+  return align_up((size_t)B * p.nsrc * p.KP * sizeof(uint32_t), 256) + 256 /* norm bound */ + align_up((size_t)B * sizeof(int32_t), 256);
 }
 
 int launch_row_norm2_max(const float* db, int N, int D, float* out, cudaStream_t s) {
@@ -729,6 +903,7 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
   Arena a(d_ws, ws_bytes);
   uint32_t* part = a.take<uint32_t>((size_t)B * p.nsrc * p.KP);
   float* norm_slot = a.take<float>(1);
+  int32_t* flagged = a.take<int32_t>((size_t)B);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "retrieve_topk: workspace %zu < %zu bytes", ws_bytes, a.used);
   T2P_REQUIRE((reinterpret_cast<uintptr_t>(d_q) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_db) & 15) == 0, T2P_ERR_INVALID,
               "retrieve_topk: q and db must be 16-byte aligned for TMA");
@@ -760,7 +935,19 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
   q.tile_n = p.tile_n; q.nb_bits = p.nb_bits; q.force_rescan = force_rescan; q.idx_base = idx_base;
   if (p.sel_smem > 48 * 1024)
     T2P_CUDA(cudaFuncSetAttribute(retrieve_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sel_smem));
-  retrieve_select_kernel<<<B, SEL_THREADS, p.sel_smem, s>>>(d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats);
+  // warp-per-query select first (the common case certifies there); the CTA-per-query kernel then only runs for flagged queries
+  const size_t selw_smem = (size_t)SELW_WARPS * p.nsrc * p.KP * sizeof(uint32_t);
+  const bool warp_path = !force_rescan && (D & 127) == 0 && D <= 256 && k <= 16 && p.nsrc <= 32 * SELW_MAX_LPL &&
+                         selw_smem <= 200 * 1024 && flagged != nullptr;
+  if (warp_path) {
+    if (selw_smem > 48 * 1024)
+      T2P_CUDA(cudaFuncSetAttribute(retrieve_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)selw_smem));
+    retrieve_select_warp_kernel<<<(B + SELW_WARPS - 1) / SELW_WARPS, 32 * SELW_WARPS, selw_smem, s>>>(
+        d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats, flagged);
+    T2P_LAUNCH_CHECK();
+  }
+  retrieve_select_kernel<<<B, SEL_THREADS, p.sel_smem, s>>>(d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats,
+                                                            warp_path ? flagged : nullptr);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

@@ -40,8 +40,8 @@ constexpr int SGT_A_PART = 2 * SGT_A_CHUNK;        // hi (or lo) of a K = 128 op
 constexpr int SGT_A_BYTES = 2 * SGT_A_PART;        // 64 KB
 constexpr int SGT_W_PART = 128 * 128;              // 16 KB: 128 output channels x 64 fp16
 constexpr int SGT_W_STAGE = 2 * SGT_W_PART;        // hi + lo
-constexpr int SGT_W_STAGES = 2;
-constexpr int SGT_KV_PITCH = SGT_D + 1;            // floats per K / V row (conflict-free column reads across rows)
+constexpr int SGT_W_STAGES = 3;
+constexpr int SGT_KV_PITCH = SGT_D + 4;            // floats per K / V row: 16-byte aligned rows (float4 reads), rows 4 banks apart
 constexpr int SGT_KV_BYTES = SGT_ROWS * SGT_KV_PITCH * 4;
 constexpr int SGT_STAGES_PER_LAYER = 20;           // q 2, k 2, v 2, merge 2, mlp0 8, mlp3 4
 constexpr int SGT_BIAS_PER_LAYER = 4 * 128 + 256 + 128;
@@ -113,8 +113,9 @@ __device__ __forceinline__ void sgt_store_unit(uint8_t* A, int chunk, int row, i
 }
 
 // A operand <- act(scale * TMEM[row, col0 + 64 half ..+64) + bias): the thread's row, its 64-column half = K chunk `half`
+// (not inlined: seven call sites per layer would otherwise bloat the kernel past the instruction cache)
 template <bool RELU>
-__device__ __forceinline__ void sgt_tmem_to_A(uint32_t tmem_row_addr, uint32_t col0, int half, int row, float scale,
+__device__ __noinline__ void sgt_tmem_to_A(uint32_t tmem_row_addr, uint32_t col0, int half, int row, float scale,
                                               const float* __restrict__ bias, uint8_t* A, float& amax) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
@@ -305,16 +306,25 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
         for (int j = 0; j < 32; ++j) q[j] = fmaf(__uint_as_float(qv[j]), SGT_UNSCALE, __ldg(bq + h * SGT_DH + j));
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < MS; ++j) {
-          float acc = 0.f;
-          if (j < sn && row_valid) {
-            const float* kr = KV + (s0 + j) * SGT_KV_PITCH + h * SGT_DH;
+        for (int j = 0; j < MS; ++j) p[hh][j] = 0.f;
+        if (row_valid) {
+#pragma unroll 1
+          for (int j = 0; j < sn; ++j) {  // dynamic loop (small code); the score lands in its static register by a select chain
+            const float4* kr = reinterpret_cast<const float4*>(KV + (s0 + j) * SGT_KV_PITCH + h * SGT_DH);
+            float acc = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc = fmaf(q[c], kr[c], acc);
+            for (int c = 0; c < 8; ++c) {
+              const float4 kk = kr[c];
+              acc = fmaf(q[4 * c], kk.x, acc);
+              acc = fmaf(q[4 * c + 1], kk.y, acc);
+              acc = fmaf(q[4 * c + 2], kk.z, acc);
+              acc = fmaf(q[4 * c + 3], kk.w, acc);
+            }
             acc *= inv_sqrt_dh;
             mx = fmaxf(mx, acc);
+#pragma unroll
+            for (int jj = 0; jj < MS; ++jj) p[hh][jj] = (jj == j) ? acc : p[hh][jj];
           }
-          p[hh][j] = acc;
         }
         float sum = 0.f;
 #pragma unroll
@@ -344,22 +354,31 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int h = 2 * half + hh;
+        float a[32];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float a[8];
+        for (int c = 0; c < 32; ++c) a[c] = 0.f;
+        if (row_valid) {
+#pragma unroll 1
+          for (int j = 0; j < sn; ++j) {
+            float pj = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) a[e] = 0.f;
+            for (int jj = 0; jj < MS; ++jj) pj = (jj == j) ? p[hh][jj] : pj;
+            const float4* vr = reinterpret_cast<const float4*>(KV + (s0 + j) * SGT_KV_PITCH + h * SGT_DH);
 #pragma unroll
-          for (int j = 0; j < MS; ++j) {
-            if (j < sn) {
-              const float* vr = KV + (s0 + j) * SGT_KV_PITCH + h * SGT_DH + 8 * u;
-              const float pj = p[hh][j];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = fmaf(pj, row_valid ? vr[e] : 0.f, a[e]);
+            for (int c = 0; c < 8; ++c) {
+              const float4 vv = vr[c];
+              a[4 * c] = fmaf(pj, vv.x, a[4 * c]);
+              a[4 * c + 1] = fmaf(pj, vv.y, a[4 * c + 1]);
+              a[4 * c + 2] = fmaf(pj, vv.z, a[4 * c + 2]);
+              a[4 * c + 3] = fmaf(pj, vv.w, a[4 * c + 3]);
             }
           }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float a8[8] = {a[8 * u], a[8 * u + 1], a[8 * u + 2], a[8 * u + 3], a[8 * u + 4], a[8 * u + 5], a[8 * u + 6], a[8 * u + 7]};
           uint4 hi4, lo4;
-          sgt_split8(a, hi4, lo4, amax);
+          sgt_split8(a8, hi4, lo4, amax);
           sgt_store_unit(A, half, row, 4 * hh + u, hi4, lo4);
         }
       }

@@ -148,25 +148,30 @@ def test_cell_embedding_independent_of_batching(coarse_model):
 
 
 def test_set_abstraction_tensor_core_equals_fp32_kernel(coarse_model):
-    """SA2 / SA3 second layer on tcgen05 (fp16 hi/lo split, csrc/sa_tc.cu) vs the exact-fp32 CUDA-core kernel: same gather
-    tables, same max; the per-layer outputs agree to fp32 rounding (the dropped lo*lo term is ~2^-22 relative)."""
+    """Every tensor-core layer of PointNet++ (second local_nn layers of SA1-3, dense first layers, global abstraction, lin1 / lin2:
+    fp16 hi/lo split, csrc/sa_tc.cu) vs the exact-fp32 CUDA-core kernels: same gather tables, same max; the per-layer outputs
+    agree to fp32 rounding (the dropped lo*lo term is ~2^-22 relative)."""
     pn = coarse_model.object_encoder.pointnet
     cells = syn.synth_packed_cells(12, 40).to("cuda")  # ~450 objects: several waves of work items per CTA
     start = obj_cell_start_from_offsets(cells.cell_offsets)
     _, desc = pn.t2p_packed()
-    assert desc.sa_l2_tc_off[1] >= 0 and desc.sa_l2_tc_off[2] >= 0 and desc.sa_l2_tc_off[0] < 0 and desc.ga_l2_tc_off >= 0
+    assert all(desc.sa_l2_tc_off[i] >= 0 for i in range(3)) and desc.ga_l2_tc_off >= 0 and all(desc.dense_tc_off[i] >= 0 for i in range(5))
     f_tc, dbg_tc = pn.features_packed(cells.pos, cells.rgb, start, debug=True)
-    saved = [desc.sa_l2_tc_off[i] for i in range(3)], desc.ga_l2_tc_off
-    try:  # the same forward with every tensor-core layer (SA2, SA3, second global-abstraction layer) on the fp32 kernels
+    saved = [desc.sa_l2_tc_off[i] for i in range(3)], desc.ga_l2_tc_off, [desc.dense_tc_off[i] for i in range(6)]
+    try:  # the same forward with every tensor-core layer on the fp32 kernels
         for i in range(3):
             desc.sa_l2_tc_off[i] = -1
+        for i in range(6):
+            desc.dense_tc_off[i] = -1
         desc.ga_l2_tc_off = -1
         f_32, dbg_32 = pn.features_packed(cells.pos, cells.rgb, start, debug=True)
     finally:
         for i in range(3):
             desc.sa_l2_tc_off[i] = saved[0][i]
+        for i in range(6):
+            desc.dense_tc_off[i] = saved[2][i]
         desc.ga_l2_tc_off = saved[1]
-    for l in (1, 2):
+    for l in (0, 1, 2):
         a, b = dbg_tc["x"][l].cpu().numpy(), dbg_32["x"][l].cpu().numpy()
         np.testing.assert_allclose(a, b, atol=1e-5 * max(1.0, float(np.abs(b).max())), rtol=1e-5)
     np.testing.assert_allclose(f_tc.cpu().numpy(), f_32.cpu().numpy(), atol=1e-5 * max(1.0, float(f_32.abs().max())), rtol=1e-5)

@@ -44,6 +44,7 @@ class PointNet2Desc(C.Structure):
         ("reserved", C.c_int32),
         ("ga_l2_tc_off", C.c_int64),
         ("sa_l2_tc_off", C.c_int64 * 3),
+        ("dense_tc_off", C.c_int64 * 6),
     ]
 
 

@@ -7,6 +7,7 @@
 """
 from typing import List
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -80,7 +81,7 @@ class CellRetrievalNetwork(PackedModule):
     def encode_cells_packed(self, cells: PackedCells, return_debug: bool = False):
         weights, desc = self.t2p_packed()
         emb = object_encoder_forward(weights, desc["pointnet"], desc["objenc"], cells, self)
-        return cell_aggregate(weights, desc["cellagg"], emb, cells.cell_offsets, self, return_debug)
+        return cell_aggregate(weights, desc["cellagg"], emb, cells.cell_offsets, self, return_debug, cells.host_offsets())
 
     def forward(self):
         raise Exception("Not implemented.")
@@ -93,14 +94,16 @@ class CellRetrievalNetwork(PackedModule):
         return next(self.lin.parameters()).device
 
 
-def cell_aggregate(weights, desc, emb: torch.Tensor, cell_offsets: torch.Tensor, owner: PackedModule, return_debug=False):
+def cell_aggregate(weights, desc, emb: torch.Tensor, cell_offsets: torch.Tensor, owner: PackedModule, return_debug=False,
+                   offsets_host=None):
+    """``offsets_host``: the same offsets as a host list (saves the device sync of reading ``cell_offsets`` back)."""
     lib = _lib.load()
     _lib.require_cuda(emb, "object embeddings")
     dev = emb.device
     n_obj, D = emb.shape
-    off_host = cell_offsets.to("cpu")
-    n_cells = off_host.numel() - 1
-    counts = off_host[1:] - off_host[:-1]
+    off_host = np.asarray(cell_offsets.tolist() if offsets_host is None else offsets_host, dtype=np.int64)
+    n_cells = off_host.size - 1
+    counts = np.diff(off_host)
     max_obj = int(counts.max()) if n_cells > 0 else 0
     if n_cells > 0 and int(counts.min()) < 1:
         raise ValueError("every cell needs at least one object")

@@ -48,6 +48,7 @@ class CellStore:
         self.raw_rgb = torch.as_tensor(raw_rgb, dtype=torch.float32).contiguous()
         self.obj_offsets = torch.as_tensor(obj_offsets, dtype=torch.int64).contiguous()
         self.cell_offsets = torch.as_tensor(cell_offsets, dtype=torch.int32).contiguous()
+        self.cell_offsets_host = self.cell_offsets.cpu()  # kept on the host: reading offsets never synchronises the device
         self.cell_ids = [str(c) for c in cell_ids]
         self.bbox_w = None if bbox_w is None else np.asarray(bbox_w, dtype=np.float64)
         self.cell_size = None if cell_size is None else np.asarray(cell_size, dtype=np.float64)
@@ -128,7 +129,7 @@ class CellStore:
         return self.slice_cells(lo, hi)
 
     def slice_cells(self, lo: int, hi: int) -> "CellStore":
-        co = self.cell_offsets.cpu()
+        co = self.cell_offsets_host
         o0, o1 = int(co[lo]), int(co[hi])
         oo = self.obj_offsets.cpu()
         p0, p1 = int(oo[o0]), int(oo[o1])
@@ -149,7 +150,7 @@ class CellStore:
         cell_hi = self.num_cells if cell_hi is None else cell_hi
         dev = self.device
         co = self.cell_offsets[cell_lo:cell_hi + 1]
-        co_host = co.cpu()
+        co_host = self.cell_offsets_host[cell_lo:cell_hi + 1]
         o0, o1 = int(co_host[0]), int(co_host[-1])
         n_obj = o1 - o0
         pos = torch.empty(n_obj, P, 3, dtype=torch.float32, device=dev)
@@ -170,7 +171,7 @@ class CellStore:
                                             _lib.ptr(ch_out), _lib.stream_ptr(dev)),
                 "batch_object_points",
             )
-        cells = PackedCells(pos, rgb, ctr, col, (co - o0).to(torch.int32))
+        cells = PackedCells(pos, rgb, ctr, col, (co - o0).to(torch.int32), [int(x) - o0 for x in co_host.tolist()])
         return (cells, ctr64, ch_out) if return_extras else cells
 
 

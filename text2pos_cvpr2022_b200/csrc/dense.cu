@@ -90,12 +90,12 @@ static int launch_linear_impl(const float* xa, int Ka, int lda, const float* xb,
 }
 
 int launch_linear(const float* x, int M, int K, int ldx, const float* W, const float* bias, int N, bool relu, float* y,
-                  int ldy, cudaStream_t s) {
-  return launch_linear_impl(x, K, ldx, nullptr, 0, 0, M, W, bias, N, relu, y, ldy, 0, s);
+                  int ldy, cudaStream_t s, const int32_t* run_if) {
+  return launch_linear_impl(x, K, ldx, nullptr, 0, 0, M, W, bias, N, relu, y, ldy, 0, s, run_if);
 }
 int launch_linear_concat(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
-                         const float* bias, int N, bool relu, float* y, int ldy, cudaStream_t s) {
-  return launch_linear_impl(xa, Ka, lda, xb, Kb, ldb, M, W, bias, N, relu, y, ldy, 0, s);
+                         const float* bias, int N, bool relu, float* y, int ldy, cudaStream_t s, const int32_t* run_if) {
+  return launch_linear_impl(xa, Ka, lda, xb, Kb, ldb, M, W, bias, N, relu, y, ldy, 0, s, run_if);
 }
 int launch_linear_groupmax(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
                            const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s,
@@ -160,7 +160,7 @@ constexpr int SA_MAX_M = 512;
 
 __global__ void __launch_bounds__(GTHREADS)
 sa_edge_kernel(const float* __restrict__ T, const float* __restrict__ S, const int32_t* __restrict__ nbr,
-               const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int P, int m,
+               const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int n_obj, int P, int m,
                int C1, const float* __restrict__ W2, const float* __restrict__ b2, int C2, float* __restrict__ out,
                const int32_t* __restrict__ run_if) {
   __shared__ GemmSmem sm;
@@ -168,10 +168,14 @@ sa_edge_kernel(const float* __restrict__ T, const float* __restrict__ S, const i
   __shared__ int incl[SA_MAX_M];
   if (run_if != nullptr && *run_if == 0) return;  // conditional re-run (block-uniform)
   __shared__ int rowT[GBM], rowS[GBM];
-  const int o = blockIdx.z, t = blockIdx.x, n0 = blockIdx.y * GBN;
+  const int t = blockIdx.x, n0 = blockIdx.y * GBN;
   const int tid = threadIdx.x;
   const int extra = quirk ? 1 : 0;
 
+  // objects blockIdx.z, blockIdx.z + gridDim.z, ...: the conditional re-run is launched with a few z-slices only, so that the
+  // usual case (flag clear) costs a handful of CTAs instead of one early-exit CTA per (object, tile)
+  for (int o = blockIdx.z; o < n_obj; o += gridDim.z) {
+  __syncthreads();  // the shared tables of the previous object are no longer read
   for (int c = tid; c < m; c += GTHREADS) incl[c] = cnt[(size_t)o * m + c] + extra;
   __syncthreads();
   for (int off = 1; off < m; off <<= 1) {  // inclusive Hillis-Steele scan, m <= 512
@@ -185,7 +189,7 @@ sa_edge_kernel(const float* __restrict__ T, const float* __restrict__ S, const i
     __syncthreads();
   }
   const int E = incl[m - 1];
-  if (t * GBM >= E) return;
+  if (t * GBM >= E) continue;
 
   if (tid < GBM) {
     const int e = t * GBM + tid;
@@ -231,6 +235,7 @@ sa_edge_kernel(const float* __restrict__ T, const float* __restrict__ S, const i
     for (int i = 0; i < 4; ++i) val[i][j] = fmaxf(acc[i][j] + b, 0.f);
   }
   tile_group_max(val, rowS, out, C2, n0, C2, rs);
+  }
 }
 
 int launch_sa_edge(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt,
@@ -240,8 +245,8 @@ int launch_sa_edge(const float* T, const float* S, const int32_t* nbr, const int
   T2P_REQUIRE(m <= SA_MAX_M, T2P_ERR_UNSUPPORTED, "set abstraction: m=%d centres per object > %d", m, SA_MAX_M);
   T2P_REQUIRE(n_obj <= 65535, T2P_ERR_UNSUPPORTED, "set abstraction: n_obj=%d > 65535 per call (chunk the cells)", n_obj);
   const int rows_max = m * (T2P_MAX_NEIGHBORS + (quirk ? 1 : 0));
-  dim3 grid((rows_max + GBM - 1) / GBM, (C2 + GBN - 1) / GBN, n_obj);
-  sa_edge_kernel<<<grid, GTHREADS, 0, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, C1, W2, b2, C2, out, run_if);
+  dim3 grid((rows_max + GBM - 1) / GBM, (C2 + GBN - 1) / GBN, run_if ? std::min(n_obj, 16) : n_obj);
+  sa_edge_kernel<<<grid, GTHREADS, 0, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, C1, W2, b2, C2, out, run_if);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

@@ -55,7 +55,7 @@ static size_t pn_carve(const PnDims& d, int n_obj, Arena& a, PnWorkspace* w) {
   w->gah = a.take<float>(n * d.Pd[3] * d.ga_h);
   w->f0 = a.take<float>(n * d.ga_o);
   w->f1 = a.take<float>(n * d.f1);
-  w->flags = a.take<int32_t>(8);
+  w->flags = a.take<int32_t>(16);
   return a.used;
 }
 
@@ -141,7 +141,23 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
   pn_carve(d, n_obj, a, &ws);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "pointnet2: workspace %zu < %zu bytes", ws_bytes, a.used);
   cudaStream_t s = as_stream(stream);
-  T2P_CUDA(cudaMemsetAsync(ws.flags, 0, 8 * sizeof(int32_t), s));  // fp16 range flags: SA1..3, global abstraction
+  T2P_CUDA(cudaMemsetAsync(ws.flags, 0, 16 * sizeof(int32_t), s));  // fp16 range flags of the tensor-core layers
+  const int sms = sm_count_cached();
+  // dense layer on the tensor cores when its images are packed (desc->dense_tc_off[i] >= 0), with the exact-fp32 kernel behind it as
+  // the conditional re-run for activations outside the fp16 range; else the fp32 kernel alone
+  auto dense = [&](int slot, const float* x, int K, int M, const t2p_linear_desc& lin, const float* pos, bool relu, float* y) -> int {
+    const float* W = wptr(w, lin.w_off);
+    const float* bias = wptr(w, lin.b_off);
+    const int N = lin.n;
+    const int32_t* run_if = nullptr;
+    if (desc->dense_tc_off[slot] >= 0 && linear_tc_supported(K, N) && (size_t)desc->dense_tc_off[slot] + (size_t)K * N <= w->n_floats) {
+      T2P_TRY(launch_linear_tc(x, K, M, K, wptr(w, desc->dense_tc_off[slot]), bias, N, pos, pos ? W + (size_t)K * N : nullptr, relu, y,
+                               sms, ws.flags + 4 + slot, s));
+      run_if = ws.flags + 4 + slot;
+    }
+    if (pos) return launch_linear_concat(x, K, K, pos, 3, 3, M, W, bias, N, relu, y, N, s, run_if);
+    return launch_linear(x, M, K, K, W, bias, N, relu, y, N, s, run_if);
+  };
 
   const float* x_in = d_rgb;
   const float* pos_in = d_pos;
@@ -150,13 +166,16 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
     const float* W1 = wptr(w, desc->sa_l1[l].w_off);
     T2P_TRY(launch_fps_ball(pos_in, n_obj, Pd, m, desc->sa_radius_sq[l], ws.ctr_idx, ws.cpos[l], ws.nbr, ws.cnt, s));
     // T_j = W1 . [x_j | pos_j] + b1 for every point;  S_c = W1[pos rows] . pos_c for every centre
-    T2P_TRY(launch_linear_concat(x_in, Cin, Cin, pos_in, 3, 3, n_obj * Pd, W1, wptr(w, desc->sa_l1[l].b_off), C1, false,
-                                 ws.T, C1, s));
+    if (l >= 1) {
+      T2P_TRY(dense(l - 1, x_in, Cin, n_obj * Pd, desc->sa_l1[l], pos_in, false, ws.T));
+    } else {
+      T2P_TRY(launch_linear_concat(x_in, Cin, Cin, pos_in, 3, 3, n_obj * Pd, W1, wptr(w, desc->sa_l1[l].b_off), C1, false,
+                                   ws.T, C1, s));
+    }
     T2P_TRY(launch_linear(ws.cpos[l], n_obj * m, 3, 3, W1 + (size_t)Cin * C1, nullptr, C1, false, ws.S, C1, s));
     T2P_CUDA(cudaMemsetAsync(ws.x[l], 0, (size_t)n_obj * m * C2 * sizeof(float), s));
     if (desc->sa_l2_tc_off[l] >= 0 && sa_edge_tc_supported(C1, C2, m) &&
-        (size_t)desc->sa_l2_tc_off[l] + (size_t)C1 * C2 <= w->n_floats) {
-      // second layer + ReLU + max on the tensor cores (fp16 hi/lo split, fp32 accumulate)
+        (size_t)desc->sa_l2_tc_off[l] + (size_t)((C1 + 63) / 64 * 64) * C2 <= w->n_floats) {
       // second layer + ReLU + max on the tensor cores (fp16 hi/lo split, fp32 accumulate).  If an activation did not fit the
       // fp16 range the kernel raises ws.flags[l] and the two launches behind it redo the layer in exact fp32 (they return
       // at once otherwise): results stay within the 1e-4 contract for any weights, at tensor-core speed for sane ones.
@@ -184,8 +203,7 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
   }
   // global abstraction: get_mlp([259,512,1024]) on cat(x,pos) then per-object max; lin1, lin2 with ReLU
   const int m3 = d.Pd[3];
-  T2P_TRY(launch_linear_concat(x_in, d.C2[2], d.C2[2], pos_in, 3, 3, n_obj * m3, wptr(w, desc->ga_l1.w_off),
-                               wptr(w, desc->ga_l1.b_off), d.ga_h, true, ws.gah, d.ga_h, s));
+  T2P_TRY(dense(2, x_in, d.C2[2], n_obj * m3, desc->ga_l1, pos_in, true, ws.gah));
   T2P_CUDA(cudaMemsetAsync(ws.f0, 0, (size_t)n_obj * d.ga_o * sizeof(float), s));
   if (desc->ga_l2_tc_off >= 0 && linear_groupmax_tc_supported(d.ga_h, d.ga_o) &&
       (size_t)desc->ga_l2_tc_off + (size_t)d.ga_h * d.ga_o <= w->n_floats) {
@@ -198,10 +216,8 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
     T2P_TRY(launch_linear_groupmax(ws.gah, d.ga_h, d.ga_h, nullptr, 0, 0, n_obj * m3, wptr(w, desc->ga_l2.w_off),
                                    wptr(w, desc->ga_l2.b_off), d.ga_o, m3, ws.f0, d.ga_o, s));
   }
-  T2P_TRY(launch_linear(ws.f0, n_obj, d.ga_o, d.ga_o, wptr(w, desc->lin1.w_off), wptr(w, desc->lin1.b_off), d.f1, true,
-                        ws.f1, d.f1, s));
-  T2P_TRY(launch_linear(ws.f1, n_obj, d.f1, d.f1, wptr(w, desc->lin2.w_off), wptr(w, desc->lin2.b_off), d.f2, true,
-                        d_features2, d.f2, s));
+  T2P_TRY(dense(3, ws.f0, d.ga_o, n_obj, desc->lin1, nullptr, true, ws.f1));
+  T2P_TRY(dense(4, ws.f1, d.f1, n_obj, desc->lin2, nullptr, true, d_features2));
   return T2P_OK;
 }
 

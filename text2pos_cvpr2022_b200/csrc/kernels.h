@@ -6,10 +6,10 @@ namespace t2p {
 
 // y[M,N] (ld ldy) = act(x[M,K] (ld ldx) . W[K,N] + bias)
 int launch_linear(const float* x, int M, int K, int ldx, const float* W, const float* bias, int N, bool relu,
-                  float* y, int ldy, cudaStream_t s);
+                  float* y, int ldy, cudaStream_t s, const int32_t* run_if = nullptr);
 // y = act([xa | xb] . W + bias): xa [M,Ka] (ld lda), xb [M,Kb] (ld ldb), K = Ka + Kb
 int launch_linear_concat(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
-                         const float* bias, int N, bool relu, float* y, int ldy, cudaStream_t s);
+                         const float* bias, int N, bool relu, float* y, int ldy, cudaStream_t s, const int32_t* run_if = nullptr);
 // out[row / rows_per_group, N] = max over the group's rows of relu([xa|xb] . W + bias); out must be zeroed
 int launch_linear_groupmax(const float* xa, int Ka, int lda, const float* xb, int Kb, int ldb, int M, const float* W,
                            const float* bias, int N, int rows_per_group, float* out, int ldo, cudaStream_t s,
@@ -39,6 +39,11 @@ int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const 
                       int quirk, int n_obj, int P, int m, int C, const float* w_img, const float* b2, float* out, int sms,
                       int32_t* overflow_flag, cudaStream_t s);
 bool linear_groupmax_tc_supported(int K, int N);
+// y[M, N] = act(x[M, K] (ld ldx, x >= 0) . W + bias + pos[M, 3] . Wp) on the tensor cores (w_img: fp16 hi/lo images of 2^8 W per
+// column block, Wp: fp32 [3, N] or NULL); supported (K, N): the dense layers of PointNet++ (see linear_tc_supported)
+bool linear_tc_supported(int K, int N);
+int launch_linear_tc(const float* x, int ldx, int M, int K, const float* w_img, const float* bias, int N, const float* pos,
+                     const float* Wp, bool relu, float* y, int sms, int32_t* overflow_flag, cudaStream_t s);
 int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, const float* bias, int N, int group, float* out,
                               int sms, int32_t* overflow_flag, cudaStream_t s);
 int launch_fps_ball(const float* pos, int n_obj, int P, int m, float r2, int32_t* ctr_idx, float* cpos,

@@ -28,9 +28,13 @@ using namespace sm100;
 
 constexpr int SAT_ROWS = 128;
 constexpr int SAT_PROD_WARPS = 8;                       // A-operand producer warps (16 rows of a chunk each)
-constexpr int SAT_EPI_WARP0 = 2 + SAT_PROD_WARPS;        // first of the 4 epilogue warps
-constexpr int SAT_THREADS = 32 * (SAT_EPI_WARP0 + 4);
-constexpr int SAT_STAGES = 2;
+constexpr int SAT_EPI_WARP0 = 2 + SAT_PROD_WARPS;        // first of the 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int SAT_EPI_WARPS = 8;
+constexpr int SAT_BUILDER2 = SAT_EPI_WARP0 + SAT_EPI_WARPS;  // second row-table warp (odd items)
+constexpr int SAT_THREADS = 32 * (SAT_BUILDER2 + 1);
+constexpr int SAT_MAX_STAGES = 4;
+constexpr int SAT_NTAB = 6;   // row tables in flight: a table lives from the builder through producers, MMA and epilogue (~4 role
+                              // latencies); with two tables at most two items were in the pipe and every role idled most of the time
 constexpr float SAT_WUNSCALE = 1.f / 256.f;
 constexpr float SAT_AMAX = 60000.f;  // activations above this do not fit fp16 (max 65504): the layer is redone in fp32
 
@@ -38,13 +42,17 @@ struct SatRows {
   int rowT[SAT_ROWS];  // row of T (global point index) feeding edge r
   int rowS[SAT_ROWS];  // row of S / of the output (global centre index), -1 = padding
   int n_valid;         // 0 = nothing to do for this item
-  int pad[3];
+  int t_row0;          // gathered mode: first row of T of this item's object (its tile in shared memory = rows [t_row0, t_row0 + P))
+  int t_seq;           // sequence number of the object among this CTA's objects (parity of the tile barriers)
+  int t_last;          // 1 = last item of its object (the producers release the tile after it)
 };
 
 struct SatBars {
-  uint64_t full[SAT_STAGES], empty[SAT_STAGES];
+  uint64_t full[SAT_MAX_STAGES], empty[SAT_MAX_STAGES];
+  uint64_t w_full;  // resident-weight mode: the whole W2 image has landed
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t rows_full[2], rows_empty[2];
+  uint64_t rows_full[SAT_NTAB], rows_empty[SAT_NTAB];
+  uint64_t t_full, t_empty;  // gathered mode: the object's T tile has landed in shared memory / all producers are done with it
   uint32_t tmem_slot;
 };
 
@@ -81,44 +89,71 @@ __host__ __device__ constexpr uint32_t sat_idesc(int M, int N) {
 // K = input channels, N = output channels of this launch's column block (blockIdx.y selects it), DENSE = false: set
 // abstraction (gathered edges, K == N == C); DENSE = true: a plain linear layer + ReLU + max over groups of `m` consecutive
 // rows (the global abstraction layer of PointNet++, models/pointcloud/pointnet2.py:45-49): rows = n_obj, T = the input.
-template <int K, int N, bool DENSE>
+// PLAIN (DENSE only): no max -- y[row, :] = act(x[row, :K] . W + b2 + pos[row, :3] . Wp) stored row by row: the first local_nn
+// layers of the set abstractions (T_j = W1 . [x_j | pos_j] + b1: the x part on the tensor cores, the 3-wide position part in
+// the epilogue), the first global-abstraction layer and lin1 / lin2.  x >= 0 is required as for DENSE (ReLU outputs / colours).
+// Gathered mode (DENSE = false): CT = channels of T / S (row pitch); K = CT rounded up to 64 (zero columns), N = this launch's
+// column block (blockIdx.y).  The T rows of ONE object (P x CT floats, contiguous) are staged in shared memory with one bulk
+// copy per object and the edge gather reads them from there: an object's tile is touched by one CTA only, and gathering 128-512
+// byte rows from L2 / HBM per edge (up to 33 edges per centre) was what bound the kernel (ncu: tensor pipe 12-24 %, 63 % of
+// the samples on the long scoreboard).  Only the flat-index self-loop rows, which may belong to another object of the cell,
+// still come from global memory.
+// NST = pipeline stages; WRES: the whole fp16 hi/lo image of W2 (K/64 chunks x 2 x N x 128 bytes) stays resident in shared
+// memory (loaded once per CTA) and the stages hold the A operand only -- re-streaming a W chunk per 128 edges put one
+// L2 round trip (~1.5 us) on every chunk of a two-stage ring.
+// TILE: stage the object's T rows in shared memory (else the producers gather every row from global memory / L2).
+template <int K, int N, bool DENSE, bool PLAIN = false, int CT = K, int NST = 2, bool WRES = false, bool TILE = false>
 __global__ void __launch_bounds__(SAT_THREADS, 1)
 sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, const int32_t* __restrict__ nbr,
                   const int32_t* __restrict__ cnt, const int32_t* __restrict__ obj_cell_start, int quirk, int P, int m,
                   int n_obj, const uint4* __restrict__ w_img, const float* __restrict__ b2,
-                  float* __restrict__ out, int ldo, int32_t* __restrict__ overflow_flag) {
-  constexpr int C = K;                           // row pitch of T / S
+                  float* __restrict__ out, int ldo, int32_t* __restrict__ overflow_flag, int ldx = K,
+                  const float* __restrict__ pos = nullptr, const float* __restrict__ Wp = nullptr, int relu_out = 1) {
+  const int C = DENSE ? ldx : CT;                // row pitch of T / S
   constexpr int NKC = K / 64;                    // 64-wide K chunks
   constexpr int A_PART = SAT_ROWS * 128;         // one of {hi, lo} of an A chunk: 128 rows x 128 bytes
   constexpr int W_PART = N * 128;                // one of {hi, lo} of a W chunk: N rows x 128 bytes
-  constexpr int STAGE_BYTES = 2 * A_PART + 2 * W_PART;
+  constexpr int STAGE_BYTES = 2 * A_PART + (WRES ? 0 : 2 * W_PART);
+  constexpr int SAT_STAGES = NST;
+  static_assert(NST >= 2 && NST <= SAT_MAX_STAGES, "2..4 stages");
   constexpr int TMEM_COLS = 2 * N;               // two accumulators
   const int n_off = (int)blockIdx.y * N;         // first output column of this CTA
   w_img += (size_t)blockIdx.y * (NKC * 2 * W_PART / 16);
   b2 += n_off;
   out += n_off;
+  if (PLAIN && Wp != nullptr) Wp += n_off;
   constexpr int EPI_PITCH = 33;                  // floats per row of the transpose buffer (32 columns + 1: conflict-free)
+  constexpr int NEH = N >= 256 ? 1 : 2;          // epilogue halves (4 warps + a 17 KB transpose buffer each): one when the W stage is 64 KB
 
   extern __shared__ __align__(1024) uint8_t sat_raw[];
   if ((smem_u32(sat_raw) & 1023u) != 0u) __trap();
   uint8_t* stages = sat_raw;
-  float* epi = reinterpret_cast<float*>(stages + SAT_STAGES * STAGE_BYTES);  // [128][33]
-  SatRows* rows = reinterpret_cast<SatRows*>(epi + SAT_ROWS * EPI_PITCH);    // [2]
-  SatBars* bars = reinterpret_cast<SatBars*>(rows + 2);
+  float* epi_all = reinterpret_cast<float*>(stages + SAT_STAGES * STAGE_BYTES);  // [2 halves][128][33]
+  SatRows* rows = reinterpret_cast<SatRows*>(epi_all + NEH * SAT_ROWS * EPI_PITCH);  // [SAT_NTAB]
+  SatBars* bars = reinterpret_cast<SatBars*>(rows + SAT_NTAB);
+  int* inclS_all = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 builders][128] edge-count prefixes
+  float* Tsm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(inclS_all) + 1024);  // TILE: [P][CT] tile of the current object
+  // resident-weight mode: [K chunk][hi|lo][N rows x 128 bytes] behind the tile, 1024-byte aligned (128-byte swizzle atoms)
+  uint8_t* Wres = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(Tsm) + (TILE ? (size_t)P * CT * 4 : 0) + 1023) & ~(uintptr_t)1023);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < SAT_STAGES; ++s) {
-      mbar_init(&bars->full[s], SAT_PROD_WARPS + 1);  // the producer warps + the expect_tx arrive of the W loader
+      mbar_init(&bars->full[s], SAT_PROD_WARPS + (WRES ? 0 : 1));  // the producer warps (+ the expect_tx arrive of the W loader)
       mbar_init(&bars->empty[s], 1);
     }
+    mbar_init(&bars->w_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 4);  // one lane per epilogue warp
-      mbar_init(&bars->rows_full[a], 1);
-      mbar_init(&bars->rows_empty[a], SAT_PROD_WARPS + 5);  // one lane of each consumer warp (MMA, producers, epilogue)
+      mbar_init(&bars->tmem_empty[a], 4 * NEH);  // one lane per (active) epilogue warp
     }
+    for (int a = 0; a < SAT_NTAB; ++a) {
+      mbar_init(&bars->rows_full[a], 1);
+      mbar_init(&bars->rows_empty[a], SAT_PROD_WARPS + 1 + 4 * NEH);  // one lane of each consumer warp (MMA, producers, epilogue)
+    }
+    mbar_init(&bars->t_full, 1);
+    mbar_init(&bars->t_empty, SAT_PROD_WARPS);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_slot);
@@ -127,15 +162,21 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_slot;
 
-  if (warp == 0) {
-    // ===== row tables, one item ahead.  Objects are dealt round-robin to the CTAs; the per-centre edge counts of an object
+  if (warp == 0 || warp == SAT_BUILDER2) {
+    // Two row-table warps in gathered mode: warp 0 builds the even items, warp SAT_BUILDER2 the odd ones (a table costs ~7,500
+    // cycles -- binary search + a dependent neighbour-list load per row -- and one warp could not keep the pipe fed); both walk
+    // all objects and items.  DENSE mode: warp 0 alone.
+    const int which = warp == 0 ? 0 : 1;
+    int* inclS = inclS_all + which * 128;
+    if (!(DENSE && which == 1)) {
+    // ===== row tables, several items ahead.  Objects are dealt round-robin to the CTAs; the per-centre edge counts of an object
     // are read once (the next object's are prefetched), its tiles are exactly ceil(E/128); a final table with
     // n_valid = -1 tells the consumers to stop. =====
     int it = 0;
     if (DENSE) {  // rows [128 tile, +128) of the n_obj input rows; output row = input row / m
       for (int tile = (int)blockIdx.x; tile * SAT_ROWS < n_obj; tile += (int)gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        const int buf = it % SAT_NTAB;
+        mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it / SAT_NTAB) & 1) ^ 1));
         SatRows* rw = rows + buf;
 #pragma unroll
         for (int rr = 0; rr < SAT_ROWS / 32; ++rr) {
@@ -149,58 +190,73 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       }
     }
     const int extra = quirk ? 1 : 0;
-    const int c0 = 2 * lane, c1 = 2 * lane + 1;
+    int oseq = 0;  // objects of this CTA staged so far
+    // per-centre edge counts of an object, four centres per lane (m <= 128): c = 4 lane + i
     int o = DENSE ? n_obj : (int)blockIdx.x;
-    int n0 = 0, n1 = 0;
+    int nc[4] = {0, 0, 0, 0};
     if (o < n_obj) {
-      n0 = c0 < m ? __ldg(cnt + (size_t)o * m + c0) + extra : 0;
-      n1 = c1 < m ? __ldg(cnt + (size_t)o * m + c1) + extra : 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nc[i] = 4 * lane + i < m ? __ldg(cnt + (size_t)o * m + 4 * lane + i) + extra : 0;
     }
     for (; o < n_obj; o += (int)gridDim.x) {
       const int o_next = o + (int)gridDim.x;
-      int p0 = 0, p1 = 0;  // prefetch of the next object's counts
+      int pn[4] = {0, 0, 0, 0};  // prefetch of the next object's counts
       if (o_next < n_obj) {
-        p0 = c0 < m ? __ldg(cnt + (size_t)o_next * m + c0) + extra : 0;
-        p1 = c1 < m ? __ldg(cnt + (size_t)o_next * m + c1) + extra : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pn[i] = 4 * lane + i < m ? __ldg(cnt + (size_t)o_next * m + 4 * lane + i) + extra : 0;
       }
-      // inclusive prefix of the per-centre edge counts (m <= 64: two entries per lane)
-      int inc = n0 + n1;
+      // inclusive prefix of the per-centre edge counts -> shared memory (only this warp reads it)
+      int inc = nc[0] + nc[1] + nc[2] + nc[3];
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, inc, off);
         if (lane >= off) inc += v;
       }
       const int E = __shfl_sync(0xffffffffu, inc, 31);
-      const int incl1 = inc, incl0 = inc - n1;  // inclusive prefix at c1, c0
+      {
+        int run = inc - (nc[0] + nc[1] + nc[2] + nc[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          run += nc[i];
+          inclS[4 * lane + i] = run;
+        }
+      }
+      __syncwarp();
       const int first = quirk ? __ldg(obj_cell_start + o) : 0;
+      if (TILE && which == 0 && E > 0) {  // stage the object's T tile: wait until the producers have released the previous object's, then ONE bulk copy
+        if (oseq > 0) mbar_wait(&bars->t_empty, (uint32_t)((oseq - 1) & 1));
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)P * CT * 4u;
+          mbar_expect_tx(&bars->t_full, bytes);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(T + (size_t)o * P * CT);
+          for (uint32_t off = 0; off < bytes; off += 16384u)
+            sat_bulk_load(smem_u32(Tsm) + off, src + off, min(16384u, bytes - off), &bars->t_full);
+        }
+        __syncwarp();
+      }
       for (int e_base = 0; e_base < E; e_base += SAT_ROWS, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        if ((it & 1) != which) continue;  // the other row-table warp's item
+        const int buf = it % SAT_NTAB;
+        mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it / SAT_NTAB) & 1) ^ 1));
         SatRows* rw = rows + buf;
 #pragma unroll
         for (int rr = 0; rr < SAT_ROWS / 32; ++rr) {
           const int r = rr * 32 + lane;
           const int e = e_base + r;
           int rt = 0, rs = -1;
-          // smallest centre c with incl[c] > e: binary search over the 2m prefix values held two per lane.  Every lane
-          // runs the same 6 rounds (m <= 64) -- the shuffles sit in convergent code -- and out-of-range rows are masked after.
-          const int ee = min(e, E - 1);
-          int lo = 0, hi = m - 1;
-#pragma unroll
-          for (int round = 0; round < 6; ++round) {
-            const int mid = (lo + hi) >> 1;
-            const int pv1 = __shfl_sync(0xffffffffu, incl1, mid >> 1), pv0 = __shfl_sync(0xffffffffu, incl0, mid >> 1);
-            const int pv = (mid & 1) ? pv1 : pv0;
-            if (lo < hi) {
-              if (pv > ee) hi = mid; else lo = mid + 1;
-            }
-          }
-          const int c = lo;
-          const int q1 = __shfl_sync(0xffffffffu, incl1, c >> 1), q0 = __shfl_sync(0xffffffffu, incl0, c >> 1);
-          const int nn1 = __shfl_sync(0xffffffffu, n1, c >> 1), nn0 = __shfl_sync(0xffffffffu, n0, c >> 1);
           if (e < E) {
-            const int incl_c = (c & 1) ? q1 : q0;
-            const int n_c = (c & 1) ? nn1 : nn0;
+            // smallest centre c with incl[c] > e (binary search over the prefix in shared memory, m <= 128: 7 rounds)
+            int lo = 0, hi = m - 1;
+#pragma unroll
+            for (int round = 0; round < 7; ++round) {
+              const int mid = (lo + hi) >> 1;
+              if (lo < hi) {
+                if (inclS[mid] > e) hi = mid; else lo = mid + 1;
+              }
+            }
+            const int c = lo;
+            const int incl_c = inclS[c];
+            const int n_c = incl_c - (c ? inclS[c - 1] : 0);
             const int slot = e - (incl_c - n_c);
             const int cn = n_c - extra;
             if (slot < cn) {
@@ -214,29 +270,46 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
           rw->rowT[r] = rt;
           rw->rowS[r] = rs;
         }
-        if (lane == 0) rw->n_valid = min(SAT_ROWS, E - e_base);
+        if (lane == 0) {
+          rw->n_valid = min(SAT_ROWS, E - e_base);
+          rw->t_row0 = o * P;
+          rw->t_seq = oseq;
+          rw->t_last = (e_base + SAT_ROWS >= E) ? 1 : 0;
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->rows_full[buf]);
       }
-      n0 = p0;
-      n1 = p1;
+      if (E > 0) ++oseq;
+      __syncwarp();  // inclS is rewritten for the next object
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nc[i] = pn[i];
     }
-    {  // terminator
-      const int buf = it & 1;
-      mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+    if (DENSE || (it & 1) == which) {  // terminator (published by the warp that owns this item index)
+      const int buf = it % SAT_NTAB;
+      mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it / SAT_NTAB) & 1) ^ 1));
       if (lane == 0) rows[buf].n_valid = -1;
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_full[buf]);
+    }
     }
   } else if (warp == 1) {
     // ===== UMMA issuer =====
     const uint32_t idesc = sat_idesc(SAT_ROWS, N);
     const uint32_t st_addr = smem_u32(stages);
+    if (WRES) {  // the whole W2 image, once
+      if (lane == 0) {
+        constexpr uint32_t WB = (uint32_t)NKC * 2u * W_PART;
+        mbar_expect_tx(&bars->w_full, WB);
+        for (uint32_t off = 0; off < WB; off += 16384u)
+          sat_bulk_load(smem_u32(Wres) + off, reinterpret_cast<const uint8_t*>(w_img) + off, min(16384u, WB - off), &bars->w_full);
+      }
+      mbar_wait(&bars->w_full, 0);
+    }
     int stage = 0, nv = 0;
     uint32_t ph = 0;
     for (int it = 0;; ++it) {
-      const int buf = it & 1;
-      mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
+      const int buf = it % SAT_NTAB;
+      mbar_wait(&bars->rows_full[buf], (uint32_t)((it / SAT_NTAB) & 1));
       const int n_valid = rows[buf].n_valid;
       if (n_valid < 0) break;
       if (n_valid > 0) {
@@ -252,7 +325,8 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {  // A_hi.W_hi, A_hi.W_lo, A_lo.W_hi
               const uint64_t a_desc = umma_desc_sw128_kmajor(sa + (prod == 2 ? A_PART : 0));
-              const uint64_t b_desc = umma_desc_sw128_kmajor(sa + 2 * A_PART + (prod == 1 ? W_PART : 0));
+              const uint64_t b_desc = umma_desc_sw128_kmajor((WRES ? smem_u32(Wres) + (uint32_t)kc * 2u * W_PART : sa + 2 * A_PART) +
+                                                             (prod == 1 ? W_PART : 0));
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 sat_umma_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | prod | ks) != 0);
@@ -276,15 +350,19 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     uint32_t ph = 0;
     float amax = 0.f;  // largest activation converted to fp16 by this lane (range guard, see the end of this branch)
     for (int it = 0;; ++it) {
-      const int buf = it & 1;
-      mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
+      const int buf = it % SAT_NTAB;
+      mbar_wait(&bars->rows_full[buf], (uint32_t)((it / SAT_NTAB) & 1));
       const SatRows* rw = rows + buf;
       if (rw->n_valid < 0) break;
       if (rw->n_valid > 0) {
+        const int t_row0 = DENSE ? 0 : rw->t_row0;
+        if (TILE) {  // the tile of this item's object (a completed phase stays complete: later items of the object pass at once)
+          mbar_wait(&bars->t_full, (uint32_t)(rw->t_seq & 1));
+        }
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait(&bars->empty[stage], ph ^ 1);
           uint8_t* st = stages + stage * STAGE_BYTES;
-          if (pw == 0 && lane == 0) {  // the W2 chunk of this K range: [hi | lo] images, contiguous in global memory
+          if (!WRES && pw == 0 && lane == 0) {  // the W2 chunk of this K range: [hi | lo] images, contiguous in global memory
             mbar_expect_tx(&bars->full[stage], 2u * W_PART);
             const uint8_t* src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)kc * (2 * W_PART);
             const uint32_t dst = smem_u32(st + 2 * A_PART);
@@ -300,16 +378,24 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
           for (int i = 0; i < RPL; ++i) {
             const int r = pw * (SAT_ROWS / SAT_PROD_WARPS) + i * 4 + rsub;
             rsv[i] = rw->rowS[r];
-            const float4* tp = reinterpret_cast<const float4*>(T + (size_t)rw->rowT[r] * C + col0);
-            tv[i][0] = rsv[i] >= 0 ? __ldg(tp) : make_float4(0.f, 0.f, 0.f, 0.f);
-            tv[i][1] = rsv[i] >= 0 ? __ldg(tp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int rt = rw->rowT[r];
+            const bool live = rsv[i] >= 0 && (DENSE || col0 < CT);  // columns >= CT are the zero padding of K
+            if (TILE && (unsigned)(rt - t_row0) < (unsigned)P) {    // the usual case: a row of this object's tile
+              const float4* tp = reinterpret_cast<const float4*>(Tsm + (size_t)(rt - t_row0) * CT + col0);
+              tv[i][0] = live ? tp[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+              tv[i][1] = live ? tp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              const float4* tp = reinterpret_cast<const float4*>(T + (size_t)rt * C + col0);
+              tv[i][0] = live ? __ldg(tp) : make_float4(0.f, 0.f, 0.f, 0.f);
+              tv[i][1] = live ? __ldg(tp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
 #pragma unroll
           for (int i = 0; i < RPL; ++i) {
             const int r = pw * (SAT_ROWS / SAT_PROD_WARPS) + i * 4 + rsub;
             const int rs = rsv[i];
             uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
-            if (rs >= 0) {
+            if (rs >= 0 && (DENSE || col0 < CT)) {
               float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
               if (!DENSE) {
                 const float4* sp = reinterpret_cast<const float4*>(S + (size_t)rs * C + col0);
@@ -342,6 +428,10 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
           if (lane == 0) mbar_arrive(&bars->full[stage]);
           if (++stage == SAT_STAGES) { stage = 0; ph ^= 1; }
         }
+        if (TILE && rw->t_last) {  // this warp has read everything it needs from the tile
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->t_empty);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_empty[buf]);
@@ -350,46 +440,73 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     // the flag makes the host-enqueued exact-fp32 kernel behind this launch recompute the layer (it is a no-op otherwise)
     if (!(amax <= SAT_AMAX) && overflow_flag) atomicOr(overflow_flag, 1);
   } else {
-    // ===== epilogue: the last four warps own TMEM lane quadrants (warp & 3); 128 threads, named barrier 1 =====
+    // ===== epilogue: eight warps, two per TMEM lane quadrant (warp & 3); half h = the 128 threads that take the 32-column
+    // groups cc = h, h + 2, ... with their own transpose buffer and named barrier.  Bias and ReLU commute with the max over
+    // the rows of a centre (both are monotone per column), so they are applied once per run, not per element. =====
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;          // TMEM lane = edge row of the tile
-    const int et = (warp - SAT_EPI_WARP0) * 32 + lane;     // 0..127: thread index inside the epilogue group
-    const int ccol = et & 31, rgrp = et >> 5;  // column pass: column of the 32-chunk, group of 32 rows
+    const int eh = (warp - SAT_EPI_WARP0) >> 2;              // half 0 / 1
+    if (eh < NEH) {
+    const int row = quad * 32 + lane;                         // TMEM lane = edge row of the tile
+    const int et = ((warp - SAT_EPI_WARP0) & 3) * 32 + lane;  // 0..127: thread index inside the half
+    const int ccol = et & 31, rgrp = et >> 5;                 // column pass: column of the 32-chunk, group of 32 rows
+    float* epi = epi_all + eh * SAT_ROWS * EPI_PITCH;
+    const int bar_id = 1 + eh;
     int nv = 0;
     for (int it = 0;; ++it) {
-      const int buf = it & 1;
-      mbar_wait(&bars->rows_full[buf], (uint32_t)((it >> 1) & 1));
+      const int buf = it % SAT_NTAB;
+      mbar_wait(&bars->rows_full[buf], (uint32_t)((it / SAT_NTAB) & 1));
       const SatRows* rw = rows + buf;
       if (rw->n_valid < 0) break;
       if (rw->n_valid > 0) {
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_full[acc], (uint32_t)((nv >> 1) & 1));
         tc_fence_after_sync();
-        for (int cc = 0; cc < N / 32; ++cc) {
+        for (int cc = eh; cc < N / 32; cc += NEH) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * N + cc * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            epi[row * EPI_PITCH + j] = fmaxf(fmaf(__uint_as_float(v[j]), SAT_WUNSCALE, __ldg(b2 + cc * 32 + j)), 0.f);
-          sat_named_barrier(1, 128);
-          // running max over the rows of a centre (contiguous), one atomic per run
-          {
-            const int r0 = rgrp * 32;
+          for (int j = 0; j < 32; ++j) epi[row * EPI_PITCH + j] = __uint_as_float(v[j]);
+          sat_named_barrier(bar_id, 128);
+          const int col = cc * 32 + ccol;
+          const float bb = __ldg(b2 + col);
+          const int r0 = rgrp * 32;
+          if (PLAIN) {
+            float wp0 = 0.f, wp1 = 0.f, wp2 = 0.f;
+            if (Wp != nullptr) {
+              wp0 = __ldg(Wp + col);
+              wp1 = __ldg(Wp + ldo + col);
+              wp2 = __ldg(Wp + 2 * ldo + col);
+            }
+            for (int r = r0; r < r0 + 32; ++r) {
+              const int rs = rw->rowS[r];
+              if (rs >= 0) {
+                float y = fmaf(epi[r * EPI_PITCH + ccol], SAT_WUNSCALE, bb);
+                if (pos != nullptr) {
+                  const float* pp = pos + (size_t)rs * 3;
+                  y = fmaf(__ldg(pp), wp0, y);
+                  y = fmaf(__ldg(pp + 1), wp1, y);
+                  y = fmaf(__ldg(pp + 2), wp2, y);
+                }
+                out[(size_t)rs * ldo + col] = relu_out ? fmaxf(y, 0.f) : y;
+              }
+            }
+          } else {
+            // running max over the rows of a centre (contiguous), one atomic per run: relu(max_r(a_r) * 2^-8 + b)
             int cur = -1;
-            float best = 0.f;
+            float best = -INFINITY;
             for (int r = r0; r < r0 + 32; ++r) {
               const int rs = rw->rowS[r];
               if (rs != cur) {
-                if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + cc * 32 + ccol, best);
+                if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + col, fmaxf(fmaf(best, SAT_WUNSCALE, bb), 0.f));
                 cur = rs;
-                best = 0.f;
+                best = -INFINITY;
               }
               if (rs >= 0) best = fmaxf(best, epi[r * EPI_PITCH + ccol]);
             }
-            if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + cc * 32 + ccol, best);
+            if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + col, fmaxf(fmaf(best, SAT_WUNSCALE, bb), 0.f));
           }
-          sat_named_barrier(1, 128);
+          sat_named_barrier(bar_id, 128);
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -399,6 +516,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_empty[buf]);
     }
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -407,33 +525,41 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
 }
 
 template <int N>
-static size_t sat_smem_bytes() {
-  return (size_t)SAT_STAGES * (2 * SAT_ROWS * 128 + 2 * N * 128) + (size_t)SAT_ROWS * 33 * sizeof(float) + 2 * sizeof(SatRows) +
-         sizeof(SatBars) + 64;
+static size_t sat_smem_bytes(size_t tile_bytes = 0, int stages = 2, size_t wres_bytes = 0) {
+  return (size_t)stages * (2 * SAT_ROWS * 128 + (wres_bytes ? 0 : 2 * N * 128)) + (N >= 256 ? 1 : 2) * (size_t)SAT_ROWS * 33 * sizeof(float) +
+         SAT_NTAB * sizeof(SatRows) + sizeof(SatBars) + 256 + 1024 + tile_bytes + (wres_bytes ? wres_bytes + 1024 : 0) + 64;
 }
 
-template <int C>
+// CT = channels of the layer (T / S pitch, output width), K = CT padded to 64, NB = column block per CTA (grid.y = CT2 / NB)
+template <int K, int NB, int CT, int NST, bool WRES, bool TILE>
 static int launch_sa_tc(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt, const int32_t* obj_cell_start,
-                        int quirk, int n_obj, int P, int m, const float* w_img, const float* b2, float* out, int sms,
+                        int quirk, int n_obj, int P, int m, int C2, const float* w_img, const float* b2, float* out, int sms,
                         int32_t* overflow_flag, cudaStream_t s) {
-  const size_t smem = sat_smem_bytes<C>();
+  const size_t smem = sat_smem_bytes<NB>(TILE ? (size_t)P * CT * sizeof(float) : 0, NST, WRES ? (size_t)(K / 64) * 2 * NB * 128 : 0);
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "set abstraction (tensor cores): %zu bytes of shared memory", smem);
-  T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<C, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(n_obj, sms);  // objects are dealt round-robin to persistent CTAs
-  sa_edge_tc_kernel<C, C, false><<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj,
-                                                                reinterpret_cast<const uint4*>(w_img), b2, out, C, overflow_flag);
+  auto kern = sa_edge_tc_kernel<K, NB, false, false, CT, NST, WRES, TILE>;
+  T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblocks = C2 / NB;
+  dim3 grid(std::max(1, std::min(n_obj, sms / nblocks)), nblocks);  // objects are dealt round-robin to persistent CTAs
+  kern<<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj, reinterpret_cast<const uint4*>(w_img), b2,
+                                       out, C2, overflow_flag, CT, nullptr, nullptr, 1);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }
 
-bool sa_edge_tc_supported(int C1, int C2, int m) { return C1 == C2 && (C1 == 128 || C1 == 256) && m <= 64; }
+bool sa_edge_tc_supported(int C1, int C2, int m) {
+  return m <= 128 && ((C1 == 32 && C2 == 64) || (C1 == 128 && C2 == 128) || (C1 == 256 && C2 == 256));
+}
 
 int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const int32_t* cnt, const int32_t* obj_cell_start,
                       int quirk, int n_obj, int P, int m, int C, const float* w_img, const float* b2, float* out, int sms,
                       int32_t* overflow_flag, cudaStream_t s) {
   if (n_obj <= 0) return T2P_OK;
-  if (C == 128) return launch_sa_tc<128>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, overflow_flag, s);
-  return launch_sa_tc<256>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, w_img, b2, out, sms, overflow_flag, s);
+  if (C == 32)  // SA1: 32 -> 64, K padded to one 64-wide chunk
+    return launch_sa_tc<64, 64, 32, 4, true, true>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 64, w_img, b2, out, sms, overflow_flag, s);
+  if (C == 128) return launch_sa_tc<128, 128, 128, 3, true, false>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 128, w_img, b2, out, sms, overflow_flag, s);
+  // SA3: two 128-column blocks per object (one CTA each), W2 streamed chunk by chunk (the 128 KB image of a block is not resident)
+  return launch_sa_tc<256, 128, 256, 2, false, false>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 256, w_img, b2, out, sms, overflow_flag, s);
 }
 
 // y[M / group, N] = max over groups of `group` consecutive rows of relu(x[M, 512] . W + b): the second layer of the global
@@ -453,6 +579,36 @@ int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, 
                                                                    reinterpret_cast<const uint4*>(w_img), bias, out, N, overflow_flag);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
+}
+
+// y[M, N] = act(x[M, K] (ld ldx, x >= 0) . W + bias + pos[M, 3] . Wp): dense layer on the tensor cores, N in column blocks of NB
+template <int K, int NB>
+static int launch_linear_tc_t(const float* x, int ldx, int M, const float* w_img, const float* bias, int N, const float* pos,
+                              const float* Wp, bool relu, float* y, int sms, int32_t* overflow_flag, cudaStream_t s) {
+  const size_t smem = sat_smem_bytes<NB>();
+  auto kern = sa_edge_tc_kernel<K, NB, true, true>;
+  T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblocks = N / NB, tiles = (M + SAT_ROWS - 1) / SAT_ROWS;
+  dim3 grid(std::max(1, std::min(tiles, sms / nblocks)), nblocks);
+  kern<<<grid, SAT_THREADS, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, M, reinterpret_cast<const uint4*>(w_img), bias,
+                                       y, N, overflow_flag, ldx, pos, Wp, relu ? 1 : 0);
+  T2P_LAUNCH_CHECK();
+  return T2P_OK;
+}
+
+bool linear_tc_supported(int K, int N) {
+  return (K == 64 && N == 128) || (K == 128 && N == 256) || (K == 256 && N == 512) || (K == 1024 && N == 512) || (K == 512 && N == 256);
+}
+
+int launch_linear_tc(const float* x, int ldx, int M, int K, const float* w_img, const float* bias, int N, const float* pos,
+                     const float* Wp, bool relu, float* y, int sms, int32_t* overflow_flag, cudaStream_t s) {
+  if (M <= 0) return T2P_OK;
+  T2P_REQUIRE(linear_tc_supported(K, N), T2P_ERR_UNSUPPORTED, "linear (tensor cores): K=%d N=%d", K, N);
+  if (K == 64) return launch_linear_tc_t<64, 128>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 128) return launch_linear_tc_t<128, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 256) return launch_linear_tc_t<256, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 1024) return launch_linear_tc_t<1024, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  return launch_linear_tc_t<512, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
 }
 
 }  // namespace t2p

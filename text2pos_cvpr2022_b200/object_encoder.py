@@ -86,6 +86,14 @@ def obj_cell_start_from_offsets(cell_offsets: torch.Tensor) -> torch.Tensor:
     return torch.repeat_interleave(cell_offsets[:-1], counts).to(torch.int32)
 
 
+def obj_cell_start_host(offsets, c0: int, c1: int, device) -> torch.Tensor:
+    """The same for cells [c0, c1) of HOST offsets, relative to the first object of the run; built on the host and copied
+    (repeat_interleave on the device would synchronise to learn its output size)."""
+    off = np.asarray(offsets[c0: c1 + 1], dtype=np.int64) - int(offsets[c0])
+    start = np.repeat(off[:-1], np.diff(off)).astype(np.int32)
+    return torch.from_numpy(start).pin_memory().to(device, non_blocking=True)
+
+
 def cell_chunks(cell_offsets_host, max_objects: int = MAX_OBJECTS_PER_CALL):
     """Split cells into runs whose object count stays <= max_objects (the quirk couples objects of a cell)."""
     chunks, start = [], 0
@@ -105,14 +113,14 @@ def object_encoder_forward(weights, pn_desc, oe_desc, cells: PackedCells, owner:
     n_obj = cells.pos.shape[0]
     D = oe_desc.embed_dim
     emb = torch.empty(n_obj, D, dtype=torch.float32, device=dev)
-    off_host = cells.cell_offsets.tolist()
+    off_host = cells.host_offsets()
     for c0, c1 in cell_chunks(off_host):
         o0, o1 = off_host[c0], off_host[c1]
         if o1 == o0:
             continue
         if o1 - o0 > 65535:
             raise RuntimeError("a single cell with more than 65535 objects is not supported")
-        start = obj_cell_start_from_offsets((cells.cell_offsets[c0 : c1 + 1] - o0).to(dev))
+        start = obj_cell_start_host(off_host, c0, c1, dev)
         f2 = pointnet2_forward(weights, pn_desc, cells.pos[o0:o1], cells.rgb[o0:o1], start, owner)
         n = o1 - o0
         with torch.cuda.device(dev):

@@ -203,16 +203,23 @@ class PackedCells:
     centers: torch.Tensor
     mean_rgb: torch.Tensor
     cell_offsets: torch.Tensor
+    offsets_host: Optional[List[int]] = None  # the same offsets on the host (kept across .to(): no device sync to read them)
 
     @property
     def num_cells(self) -> int:
         return self.cell_offsets.numel() - 1
 
+    def host_offsets(self) -> List[int]:
+        if self.offsets_host is None:
+            self.offsets_host = [int(x) for x in self.cell_offsets.tolist()]
+        return self.offsets_host
+
     def to(self, device):
-        return PackedCells(*(t.to(device) for t in (self.pos, self.rgb, self.centers, self.mean_rgb, self.cell_offsets)))
+        host = self.host_offsets() if not self.cell_offsets.is_cuda else self.offsets_host
+        return PackedCells(*(t.to(device) for t in (self.pos, self.rgb, self.centers, self.mean_rgb, self.cell_offsets)), host)
 
     def cell_slices(self):
-        off = self.cell_offsets.tolist()
+        off = self.host_offsets()
         return [(off[i], off[i + 1]) for i in range(len(off) - 1)]
 
 

@@ -149,13 +149,14 @@ typedef struct {
   int32_t self_loop_quirk; /* PointConv(add_self_loops=True) flat-index self loops, see oracle/pointnet.py */
   int32_t reserved;
   int64_t ga_l2_tc_off;    /* or -1: the same images for the second global-abstraction layer (K = 512, N = 1024), one set per
-                              256-wide column block: [N/256][K chunk 8][hi|lo][row n 256][64 fp16 swizzled] */
+                              128-wide column block: [N/128][K chunk 8][hi|lo][row n 128][64 fp16 swizzled] */
   int64_t sa_l2_tc_off[3]; /* per SA layer, or -1: fp16 hi/lo images of 2^8 * (BN-folded second layer) for the tensor-core
                               kernel (csrc/sa_tc.cu): [column block][K chunk][hi|lo][row n = output channel of the block][64
-                              fp16, k = 64*chunk + e, 16-byte units XOR-swizzled by (n & 7)]; sa1 (32 -> 64): one block of 64,
-                              K zero-padded to one chunk; sa2 (128 -> 128): one block, 2 chunks; sa3 (256 -> 256): two blocks
-                              of 128 columns, 4 chunks each */
-  int64_t dense_tc_off[6]; /* or -1: the same images (one set per column block: 128 wide for N = 128, else 256) for the x part of
+                              fp16, k = 64*chunk + e, 16-byte units XOR-swizzled by (n & 7)]; a block is always 128 output
+                              channels (the UMMA M of the transposed product): sa1 (32 -> 64): one block zero-padded to 128
+                              channels, K zero-padded to one chunk; sa2 (128 -> 128): one block, 2 chunks; sa3 (256 -> 256): two
+                              blocks, 4 chunks each */
+  int64_t dense_tc_off[6]; /* or -1: the same images (one set per 128-wide column block) for the x part of
                               the dense layers: [0] sa2 first layer (64 -> 128), [1] sa3 first layer (128 -> 256), [2] first
                               global-abstraction layer (256 -> 512), [3] lin1 (1024 -> 512), [4] lin2 (512 -> 256), [5] unused.
                               The 3-wide position part of [0]..[2] stays fp32 (added in the epilogue from the [K, N] matrix) */

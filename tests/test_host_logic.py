@@ -229,8 +229,8 @@ def test_sa_tensor_core_images_layout_and_split():
 
 
 def test_pointnet_pack_emits_tensor_core_images():
-    """pack_pointnet2: every second local_nn layer (SA1 32 -> 64 with K zero-padded to 64, SA2 128 -> 128, SA3 256 -> 256 as two
-    128-column blocks), the second global-abstraction layer (512 -> 1024, four 256-wide column blocks) and the x parts of the
+    """pack_pointnet2: every second local_nn layer (SA1 32 -> 64 zero-padded to [64, 128], SA2 128 -> 128, SA3 256 -> 256 as two
+    128-column blocks), the second global-abstraction layer (512 -> 1024, eight 128-wide column blocks) and the x parts of the
     dense layers get fp16 hi/lo images.  Image (k, n) of column block j equals the folded weight the fp32 kernels read from the
     same blob."""
     from text2pos_cvpr2022_b200.pointnet2 import PointNet2
@@ -243,9 +243,10 @@ def test_pointnet_pack_emits_tensor_core_images():
     blob = bb.finish().numpy()
     assert d.sa_l2_tc_off[0] >= 0 and d.sa_l2_tc_off[1] >= 0 and d.sa_l2_tc_off[2] >= 0 and d.ga_l2_tc_off >= 0
     assert all(d.dense_tc_off[i] >= 0 for i in range(5)) and d.dense_tc_off[5] == -1
-    # SA1: [1 chunk][hi|lo][64 rows][64 fp16], k >= 32 zero
+    # SA1: [1 chunk][hi|lo][128 rows (64 real channels)][64 fp16], k >= 32 zero
     w1 = blob[d.sa_l2[0].w_off: d.sa_l2[0].w_off + 32 * 64].astype(np.float64).reshape(32, 64)
-    img1 = blob[d.sa_l2_tc_off[0]: d.sa_l2_tc_off[0] + 64 * 64].view(np.uint32).view(np.float16).reshape(1, 2, 64, 64)
+    img1 = blob[d.sa_l2_tc_off[0]: d.sa_l2_tc_off[0] + 64 * 128].view(np.uint32).view(np.float16).reshape(1, 2, 128, 64)
+    assert float(np.abs(img1[0, :, 64:]).max()) == 0.0  # padded output channels
     for (k, n) in [(0, 0), (31, 63), (7, 20)]:
         pu = (k // 8) ^ (n & 7)
         assert float(img1[0, 0, n, pu * 8 + k % 8]) == float(np.float16(w1[k, n] * 256.0))
@@ -259,9 +260,9 @@ def test_pointnet_pack_emits_tensor_core_images():
     K, N = d.ga_l2.k, d.ga_l2.n
     assert (K, N) == (512, 1024)
     w = blob[d.ga_l2.w_off: d.ga_l2.w_off + K * N].astype(np.float64).reshape(K, N)
-    img = blob[d.ga_l2_tc_off: d.ga_l2_tc_off + K * N].view(np.uint32).view(np.float16).reshape(N // 256, K // 64, 2, 256, 64)
+    img = blob[d.ga_l2_tc_off: d.ga_l2_tc_off + K * N].view(np.uint32).view(np.float16).reshape(N // 128, K // 64, 2, 128, 64)
     for (k, n) in [(0, 0), (511, 1023), (70, 300), (129, 777)]:
-        j, nn = n // 256, n % 256
+        j, nn = n // 128, n % 128
         chunk, lu, e = k // 64, (k % 64) // 8, k % 8
         pu = lu ^ (nn & 7)
         v = w[k, n] * 256.0

@@ -175,7 +175,7 @@ int t2p_pointnet2_forward(const t2p_weights* w, const t2p_pointnet2_desc* desc, 
     T2P_TRY(launch_linear(ws.cpos[l], n_obj * m, 3, 3, W1 + (size_t)Cin * C1, nullptr, C1, false, ws.S, C1, s));
     T2P_CUDA(cudaMemsetAsync(ws.x[l], 0, (size_t)n_obj * m * C2 * sizeof(float), s));
     if (desc->sa_l2_tc_off[l] >= 0 && sa_edge_tc_supported(C1, C2, m) &&
-        (size_t)desc->sa_l2_tc_off[l] + (size_t)((C1 + 63) / 64 * 64) * C2 <= w->n_floats) {
+        (size_t)desc->sa_l2_tc_off[l] + (size_t)((C1 + 63) / 64 * 64) * ((C2 + 127) / 128 * 128) <= w->n_floats) {
       // second layer + ReLU + max on the tensor cores (fp16 hi/lo split, fp32 accumulate).  If an activation did not fit the
       // fp16 range the kernel raises ws.flags[l] and the two launches behind it redo the layer in exact fp32 (they return
       // at once otherwise): results stay within the 1e-4 contract for any weights, at tensor-core speed for sane ones.

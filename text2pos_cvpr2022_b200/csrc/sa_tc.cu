@@ -13,8 +13,14 @@
 //   warps 2-9   produce the A operand: gather T_j (coalesced 32-byte pieces, 4 rows per warp instruction), subtract S_c,
 //               ReLU, split into fp16 hi/lo, store into the 128-byte-swizzled K-major UMMA layout; warp 2 also streams the
 //               W2 chunk (host-packed hi/lo images of 2^8.W2, cp.async.bulk) into the same stage;
-//   warps 10-13 epilogue: tcgen05.ld 32 columns at a time, *2^-8 + bias, ReLU, transpose through shared memory, running
-//               max over the rows of a centre (rows of a centre are contiguous), one atomicMax per (centre, column, tile).
+//   warps 10-17 epilogue.  The product is TRANSPOSED -- D[channel][edge] = W2^T . A^T, i.e. the weight image is the UMMA "A"
+//               operand (M = 128 output channels of this CTA's column block) and the activations the "B" operand (N = 128 edges) --
+//               so a TMEM lane is an output channel and the columns are the edges: each epilogue thread owns one channel, reads
+//               32 edges at a time with tcgen05.ld and keeps the running max over the (contiguous) edges of a centre in a register;
+//               the centre boundaries are the same for every thread (warp-uniform control flow), bias + ReLU are applied once per
+//               run (they commute with the max), and the 32 lanes of a warp store 32 consecutive channels (one coalesced atomicMax
+//               per run).  No transpose through shared memory, no barrier.  (The row-major variant spent ~12,000 cycles per
+//               128-edge item in the epilogue and bounded the kernel.)
 // Two pipeline stages (A chunk 32 KB + W chunk 2*C*128 B each), two TMEM accumulators (epilogue of item i overlaps the
 // MMAs of item i+1), two row tables.  No edge tensor in HBM, no scatter.
 #include <cuda_fp16.h>
@@ -116,20 +122,19 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
   constexpr int STAGE_BYTES = 2 * A_PART + (WRES ? 0 : 2 * W_PART);
   constexpr int SAT_STAGES = NST;
   static_assert(NST >= 2 && NST <= SAT_MAX_STAGES, "2..4 stages");
-  constexpr int TMEM_COLS = 2 * N;               // two accumulators
+  static_assert(N == 128, "the column block of a CTA = UMMA M = 128 output channels");
+  constexpr int TMEM_COLS = 2 * SAT_ROWS;        // two accumulators of 128 columns (= edges) each
   const int n_off = (int)blockIdx.y * N;         // first output column of this CTA
   w_img += (size_t)blockIdx.y * (NKC * 2 * W_PART / 16);
   b2 += n_off;
   out += n_off;
   if (PLAIN && Wp != nullptr) Wp += n_off;
-  constexpr int EPI_PITCH = 33;                  // floats per row of the transpose buffer (32 columns + 1: conflict-free)
-  constexpr int NEH = N >= 256 ? 1 : 2;          // epilogue halves (4 warps + a 17 KB transpose buffer each): one when the W stage is 64 KB
+  constexpr int NEH = 2;                         // epilogue halves: 4 warps each, half h takes the 32-edge groups h, h + 2
 
   extern __shared__ __align__(1024) uint8_t sat_raw[];
   if ((smem_u32(sat_raw) & 1023u) != 0u) __trap();
   uint8_t* stages = sat_raw;
-  float* epi_all = reinterpret_cast<float*>(stages + SAT_STAGES * STAGE_BYTES);  // [2 halves][128][33]
-  SatRows* rows = reinterpret_cast<SatRows*>(epi_all + NEH * SAT_ROWS * EPI_PITCH);  // [SAT_NTAB]
+  SatRows* rows = reinterpret_cast<SatRows*>(stages + SAT_STAGES * STAGE_BYTES);  // [SAT_NTAB]
   SatBars* bars = reinterpret_cast<SatBars*>(rows + SAT_NTAB);
   int* inclS_all = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 builders][128] edge-count prefixes
   float* Tsm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(inclS_all) + 1024);  // TILE: [P][CT] tile of the current object
@@ -239,36 +244,55 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
         const int buf = it % SAT_NTAB;
         mbar_wait(&bars->rows_empty[buf], (uint32_t)(((it / SAT_NTAB) & 1) ^ 1));
         SatRows* rw = rows + buf;
+        {
+          // Four rows per lane, in PHASES so that the loads of the four rows overlap (a branchy per-row body serialised a
+          // binary search and a dependent global load per row: ~8,600 cycles per table): (1) the four binary searches over the
+          // prefix in shared memory run interleaved, (2) the four neighbour-list loads are issued together (clamped addresses,
+          // no branch), (3) the rows are written.
+          constexpr int RPLB = SAT_ROWS / 32;
+          int lo[RPLB], hi[RPLB], ee[RPLB];
 #pragma unroll
-        for (int rr = 0; rr < SAT_ROWS / 32; ++rr) {
-          const int r = rr * 32 + lane;
-          const int e = e_base + r;
-          int rt = 0, rs = -1;
-          if (e < E) {
-            // smallest centre c with incl[c] > e (binary search over the prefix in shared memory, m <= 128: 7 rounds)
-            int lo = 0, hi = m - 1;
+          for (int rr = 0; rr < RPLB; ++rr) {
+            ee[rr] = min(e_base + rr * 32 + lane, E - 1);
+            lo[rr] = 0;
+            hi[rr] = m - 1;
+          }
 #pragma unroll
-            for (int round = 0; round < 7; ++round) {
-              const int mid = (lo + hi) >> 1;
-              if (lo < hi) {
-                if (inclS[mid] > e) hi = mid; else lo = mid + 1;
-              }
+          for (int round = 0; round < 7; ++round) {  // smallest centre c with incl[c] > e (m <= 128: 7 rounds)
+            int pv[RPLB];
+#pragma unroll
+            for (int rr = 0; rr < RPLB; ++rr) pv[rr] = inclS[(lo[rr] + hi[rr]) >> 1];
+#pragma unroll
+            for (int rr = 0; rr < RPLB; ++rr) {
+              const int mid = (lo[rr] + hi[rr]) >> 1;
+              const bool go = lo[rr] < hi[rr];
+              const bool left = pv[rr] > ee[rr];
+              hi[rr] = (go && left) ? mid : hi[rr];
+              lo[rr] = (go && !left) ? mid + 1 : lo[rr];
             }
-            const int c = lo;
+          }
+          int slot[RPLB], cn[RPLB], nb[RPLB];
+#pragma unroll
+          for (int rr = 0; rr < RPLB; ++rr) {
+            const int c = lo[rr];
             const int incl_c = inclS[c];
             const int n_c = incl_c - (c ? inclS[c - 1] : 0);
-            const int slot = e - (incl_c - n_c);
-            const int cn = n_c - extra;
-            if (slot < cn) {
-              rt = o * P + __ldg(nbr + ((size_t)o * m + c) * T2P_MAX_NEIGHBORS + slot);
-            } else {  // flat-index self loop (see sa_edge_kernel)
-              const int flat = (o - first) * m + c;
-              rt = (first + flat / P) * P + flat % P;
-            }
-            rs = o * m + c;
+            slot[rr] = ee[rr] - (incl_c - n_c);
+            cn[rr] = n_c - extra;
           }
-          rw->rowT[r] = rt;
-          rw->rowS[r] = rs;
+#pragma unroll
+          for (int rr = 0; rr < RPLB; ++rr)  // clamped: a self-loop row reads a valid (unused) entry
+            nb[rr] = __ldg(nbr + ((size_t)o * m + lo[rr]) * T2P_MAX_NEIGHBORS + min(max(slot[rr], 0), T2P_MAX_NEIGHBORS - 1));
+#pragma unroll
+          for (int rr = 0; rr < RPLB; ++rr) {
+            const int r = rr * 32 + lane;
+            const int c = lo[rr];
+            const int flat = (o - first) * m + c;  // flat-index self loop (see sa_edge_kernel)
+            const int self_row = (first + flat / P) * P + flat % P;
+            const bool live = e_base + r < E;
+            rw->rowT[r] = live ? (slot[rr] < cn[rr] ? o * P + nb[rr] : self_row) : 0;
+            rw->rowS[r] = live ? o * m + c : -1;
+          }
         }
         if (lane == 0) {
           rw->n_valid = min(SAT_ROWS, E - e_base);
@@ -294,7 +318,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     }
   } else if (warp == 1) {
     // ===== UMMA issuer =====
-    const uint32_t idesc = sat_idesc(SAT_ROWS, N);
+    const uint32_t idesc = sat_idesc(N, SAT_ROWS);  // M = output channels, N = edges
     const uint32_t st_addr = smem_u32(stages);
     if (WRES) {  // the whole W2 image, once
       if (lane == 0) {
@@ -316,20 +340,20 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_empty[acc], (uint32_t)(((nv >> 1) & 1) ^ 1));
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * N;
+        const uint32_t d_tmem = tmem_base + acc * SAT_ROWS;
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait(&bars->full[stage], ph);
           tc_fence_after_sync();
           if (sat_elect_one()) {
             const uint32_t sa = st_addr + stage * STAGE_BYTES;
 #pragma unroll
-            for (int prod = 0; prod < 3; ++prod) {  // A_hi.W_hi, A_hi.W_lo, A_lo.W_hi
-              const uint64_t a_desc = umma_desc_sw128_kmajor(sa + (prod == 2 ? A_PART : 0));
-              const uint64_t b_desc = umma_desc_sw128_kmajor((WRES ? smem_u32(Wres) + (uint32_t)kc * 2u * W_PART : sa + 2 * A_PART) +
+            for (int prod = 0; prod < 3; ++prod) {  // W_hi.A_hi, W_lo.A_hi, W_hi.A_lo  (transposed product: W is the "A" operand)
+              const uint64_t act_desc = umma_desc_sw128_kmajor(sa + (prod == 2 ? A_PART : 0));
+              const uint64_t w_desc = umma_desc_sw128_kmajor((WRES ? smem_u32(Wres) + (uint32_t)kc * 2u * W_PART : sa + 2 * A_PART) +
                                                              (prod == 1 ? W_PART : 0));
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                sat_umma_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | prod | ks) != 0);
+                sat_umma_ss(d_tmem, w_desc + 2 * ks, act_desc + 2 * ks, idesc, (kc | prod | ks) != 0);
             }
             umma_commit(&bars->empty[stage]);
             if (kc == NKC - 1) umma_commit(&bars->tmem_full[acc]);
@@ -372,7 +396,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
           // all T loads of this lane (4 rows x 32 bytes) are issued before the first use: one L2 round trip per chunk
           // instead of one per row; the S rows repeat from row to row (a centre has up to 33 edges) and hit L1
           constexpr int RPL = SAT_ROWS / SAT_PROD_WARPS / 4;  // rows per lane and chunk
-          float4 tv[RPL][2];
+          float4 tv[RPL][2], sv[RPL][2];
           int rsv[RPL];
 #pragma unroll
           for (int i = 0; i < RPL; ++i) {
@@ -389,6 +413,12 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
               tv[i][0] = live ? __ldg(tp) : make_float4(0.f, 0.f, 0.f, 0.f);
               tv[i][1] = live ? __ldg(tp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            sv[i][0] = sv[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!DENSE && live) {  // the centre's S row: issued with the T loads (one memory round trip per chunk, not two)
+              const float4* sp = reinterpret_cast<const float4*>(S + (size_t)rsv[i] * C + col0);
+              sv[i][0] = __ldg(sp);
+              sv[i][1] = __ldg(sp + 1);
+            }
           }
 #pragma unroll
           for (int i = 0; i < RPL; ++i) {
@@ -396,12 +426,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
             const int rs = rsv[i];
             uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
             if (rs >= 0 && (DENSE || col0 < CT)) {
-              float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-              if (!DENSE) {
-                const float4* sp = reinterpret_cast<const float4*>(S + (size_t)rs * C + col0);
-                s0 = __ldg(sp);
-                s1 = __ldg(sp + 1);
-              }
+              const float4 s0 = sv[i][0], s1 = sv[i][1];
               const float4 t0 = tv[i][0], t1 = tv[i][1];
               const float a[8] = {fmaxf(t0.x - s0.x, 0.f), fmaxf(t0.y - s0.y, 0.f), fmaxf(t0.z - s0.z, 0.f), fmaxf(t0.w - s0.w, 0.f),
                                   fmaxf(t1.x - s1.x, 0.f), fmaxf(t1.y - s1.y, 0.f), fmaxf(t1.z - s1.z, 0.f), fmaxf(t1.w - s1.w, 0.f)};
@@ -440,17 +465,19 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
     // the flag makes the host-enqueued exact-fp32 kernel behind this launch recompute the layer (it is a no-op otherwise)
     if (!(amax <= SAT_AMAX) && overflow_flag) atomicOr(overflow_flag, 1);
   } else {
-    // ===== epilogue: eight warps, two per TMEM lane quadrant (warp & 3); half h = the 128 threads that take the 32-column
-    // groups cc = h, h + 2, ... with their own transpose buffer and named barrier.  Bias and ReLU commute with the max over
-    // the rows of a centre (both are monotone per column), so they are applied once per run, not per element. =====
+    // ===== epilogue (transposed product): eight warps, two per TMEM lane quadrant (warp & 3); lane = output channel; half h
+    // takes the 32-edge column groups cc = h, h + 2 of every item =====
     const int quad = warp & 3;
-    const int eh = (warp - SAT_EPI_WARP0) >> 2;              // half 0 / 1
-    if (eh < NEH) {
-    const int row = quad * 32 + lane;                         // TMEM lane = edge row of the tile
-    const int et = ((warp - SAT_EPI_WARP0) & 3) * 32 + lane;  // 0..127: thread index inside the half
-    const int ccol = et & 31, rgrp = et >> 5;                 // column pass: column of the 32-chunk, group of 32 rows
-    float* epi = epi_all + eh * SAT_ROWS * EPI_PITCH;
-    const int bar_id = 1 + eh;
+    const int eh = (warp - SAT_EPI_WARP0) >> 2;
+    const int ch = quad * 32 + lane;             // channel inside this CTA's column block
+    const bool ch_ok = n_off + ch < ldo;         // (sa1: the block is padded from 64 to 128 channels)
+    const float bb = ch_ok ? __ldg(b2 + ch) : 0.f;
+    float wp0 = 0.f, wp1 = 0.f, wp2 = 0.f;
+    if (PLAIN && Wp != nullptr && ch_ok) {
+      wp0 = __ldg(Wp + ch);
+      wp1 = __ldg(Wp + ldo + ch);
+      wp2 = __ldg(Wp + 2 * ldo + ch);
+    }
     int nv = 0;
     for (int it = 0;; ++it) {
       const int buf = it % SAT_NTAB;
@@ -461,52 +488,48 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
         const int acc = nv & 1;
         mbar_wait(&bars->tmem_full[acc], (uint32_t)((nv >> 1) & 1));
         tc_fence_after_sync();
-        for (int cc = eh; cc < N / 32; cc += NEH) {
+        for (int cc = eh; cc < SAT_ROWS / 32; cc += NEH) {
+          if (cc * 32 >= rw->n_valid) break;  // warp-uniform: no edge in this group
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * N + cc * 32, v);
-          tmem_ld_wait();
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * SAT_ROWS + cc * 32, v);
+          int rsv[32];  // the centres (output rows) of these 32 edges: the same for every thread
 #pragma unroll
-          for (int j = 0; j < 32; ++j) epi[row * EPI_PITCH + j] = __uint_as_float(v[j]);
-          sat_named_barrier(bar_id, 128);
-          const int col = cc * 32 + ccol;
-          const float bb = __ldg(b2 + col);
-          const int r0 = rgrp * 32;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int4 t4 = *reinterpret_cast<const int4*>(&rw->rowS[cc * 32 + 4 * j4]);
+            rsv[4 * j4] = t4.x; rsv[4 * j4 + 1] = t4.y; rsv[4 * j4 + 2] = t4.z; rsv[4 * j4 + 3] = t4.w;
+          }
+          tmem_ld_wait();
           if (PLAIN) {
-            float wp0 = 0.f, wp1 = 0.f, wp2 = 0.f;
-            if (Wp != nullptr) {
-              wp0 = __ldg(Wp + col);
-              wp1 = __ldg(Wp + ldo + col);
-              wp2 = __ldg(Wp + 2 * ldo + col);
-            }
-            for (int r = r0; r < r0 + 32; ++r) {
-              const int rs = rw->rowS[r];
-              if (rs >= 0) {
-                float y = fmaf(epi[r * EPI_PITCH + ccol], SAT_WUNSCALE, bb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int rs = rsv[j];
+              if (rs >= 0) {  // warp-uniform
+                float y = fmaf(__uint_as_float(v[j]), SAT_WUNSCALE, bb);
                 if (pos != nullptr) {
                   const float* pp = pos + (size_t)rs * 3;
                   y = fmaf(__ldg(pp), wp0, y);
                   y = fmaf(__ldg(pp + 1), wp1, y);
                   y = fmaf(__ldg(pp + 2), wp2, y);
                 }
-                out[(size_t)rs * ldo + col] = relu_out ? fmaxf(y, 0.f) : y;
+                if (ch_ok) out[(size_t)rs * ldo + ch] = relu_out ? fmaxf(y, 0.f) : y;
               }
             }
           } else {
-            // running max over the rows of a centre (contiguous), one atomic per run: relu(max_r(a_r) * 2^-8 + b)
+            // running max over the edges of a centre (contiguous columns), one atomic per run: relu(max(a) * 2^-8 + b)
             int cur = -1;
             float best = -INFINITY;
-            for (int r = r0; r < r0 + 32; ++r) {
-              const int rs = rw->rowS[r];
-              if (rs != cur) {
-                if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + col, fmaxf(fmaf(best, SAT_WUNSCALE, bb), 0.f));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int rs = rsv[j];
+              if (rs != cur) {  // warp-uniform
+                if (cur >= 0 && ch_ok) atomic_max_nonneg(out + (size_t)cur * ldo + ch, fmaxf(fmaf(best, SAT_WUNSCALE, bb), 0.f));
                 cur = rs;
                 best = -INFINITY;
               }
-              if (rs >= 0) best = fmaxf(best, epi[r * EPI_PITCH + ccol]);
+              if (rs >= 0) best = fmaxf(best, __uint_as_float(v[j]));
             }
-            if (cur >= 0) atomic_max_nonneg(out + (size_t)cur * ldo + col, fmaxf(fmaf(best, SAT_WUNSCALE, bb), 0.f));
+            if (cur >= 0 && ch_ok) atomic_max_nonneg(out + (size_t)cur * ldo + ch, fmaxf(fmaf(best, SAT_WUNSCALE, bb), 0.f));
           }
-          sat_named_barrier(bar_id, 128);
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -515,7 +538,6 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->rows_empty[buf]);
-    }
     }
   }
   tc_fence_before_sync();
@@ -526,8 +548,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
 
 template <int N>
 static size_t sat_smem_bytes(size_t tile_bytes = 0, int stages = 2, size_t wres_bytes = 0) {
-  return (size_t)stages * (2 * SAT_ROWS * 128 + (wres_bytes ? 0 : 2 * N * 128)) + (N >= 256 ? 1 : 2) * (size_t)SAT_ROWS * 33 * sizeof(float) +
-         SAT_NTAB * sizeof(SatRows) + sizeof(SatBars) + 256 + 1024 + tile_bytes + (wres_bytes ? wres_bytes + 1024 : 0) + 64;
+  return (size_t)stages * (2 * SAT_ROWS * 128 + (wres_bytes ? 0 : 2 * N * 128)) + SAT_NTAB * sizeof(SatRows) + sizeof(SatBars) + 256 + 1024 + tile_bytes + (wres_bytes ? wres_bytes + 1024 : 0) + 64;
 }
 
 // CT = channels of the layer (T / S pitch, output width), K = CT padded to 64, NB = column block per CTA (grid.y = CT2 / NB)
@@ -539,7 +560,7 @@ static int launch_sa_tc(const float* T, const float* S, const int32_t* nbr, cons
   T2P_REQUIRE(smem <= 227 * 1024, T2P_ERR_UNSUPPORTED, "set abstraction (tensor cores): %zu bytes of shared memory", smem);
   auto kern = sa_edge_tc_kernel<K, NB, false, false, CT, NST, WRES, TILE>;
   T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nblocks = C2 / NB;
+  const int nblocks = (C2 + NB - 1) / NB;
   dim3 grid(std::max(1, std::min(n_obj, sms / nblocks)), nblocks);  // objects are dealt round-robin to persistent CTAs
   kern<<<grid, SAT_THREADS, smem, s>>>(T, S, nbr, cnt, obj_cell_start, quirk, P, m, n_obj, reinterpret_cast<const uint4*>(w_img), b2,
                                        out, C2, overflow_flag, CT, nullptr, nullptr, 1);
@@ -556,37 +577,39 @@ int launch_sa_edge_tc(const float* T, const float* S, const int32_t* nbr, const 
                       int32_t* overflow_flag, cudaStream_t s) {
   if (n_obj <= 0) return T2P_OK;
   if (C == 32)  // SA1: 32 -> 64, K padded to one 64-wide chunk
-    return launch_sa_tc<64, 64, 32, 4, true, true>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 64, w_img, b2, out, sms, overflow_flag, s);
-  if (C == 128) return launch_sa_tc<128, 128, 128, 3, true, false>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 128, w_img, b2, out, sms, overflow_flag, s);
+    return launch_sa_tc<64, 128, 32, 4, true, true>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 64, w_img, b2, out, sms, overflow_flag, s);
+  if (C == 128) return launch_sa_tc<128, 128, 128, 4, true, false>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 128, w_img, b2, out, sms, overflow_flag, s);
   // SA3: two 128-column blocks per object (one CTA each), W2 streamed chunk by chunk (the 128 KB image of a block is not resident)
-  return launch_sa_tc<256, 128, 256, 2, false, false>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 256, w_img, b2, out, sms, overflow_flag, s);
+  return launch_sa_tc<256, 128, 256, 3, false, false>(T, S, nbr, cnt, obj_cell_start, quirk, n_obj, P, m, 256, w_img, b2, out, sms, overflow_flag, s);
 }
 
 // y[M / group, N] = max over groups of `group` consecutive rows of relu(x[M, 512] . W + b): the second layer of the global
 // abstraction MLP (512 -> 1024, pooled over the 32 points of an object).  x >= 0 is required (it is a ReLU output): the
 // producers apply relu(x - 0).  `out` must be zero-filled.  N is processed in column blocks of 256 (blockIdx.y).
-bool linear_groupmax_tc_supported(int K, int N) { return K == 512 && N % 256 == 0 && N >= 256; }
+bool linear_groupmax_tc_supported(int K, int N) { return K == 512 && N % 128 == 0 && N >= 128; }
 
 int launch_linear_groupmax_tc(const float* x, int M, int K, const float* w_img, const float* bias, int N, int group, float* out,
                               int sms, int32_t* overflow_flag, cudaStream_t s) {
   if (M <= 0) return T2P_OK;
   T2P_REQUIRE(linear_groupmax_tc_supported(K, N) && group >= 1, T2P_ERR_UNSUPPORTED, "linear_groupmax (tensor cores): K=%d N=%d", K, N);
-  const size_t smem = sat_smem_bytes<256>();
-  T2P_CUDA(cudaFuncSetAttribute(sa_edge_tc_kernel<512, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nblocks = N / 256, tiles = (M + SAT_ROWS - 1) / SAT_ROWS;
+  const size_t smem = sat_smem_bytes<128>(0, 3);
+  auto kern = sa_edge_tc_kernel<512, 128, true, false, 512, 3, false, false>;
+  T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblocks = N / 128, tiles = (M + SAT_ROWS - 1) / SAT_ROWS;
   dim3 grid(std::max(1, std::min(tiles, sms / nblocks)), nblocks);
-  sa_edge_tc_kernel<512, 256, true><<<grid, SAT_THREADS, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, 0, 0, group, M,
-                                                                   reinterpret_cast<const uint4*>(w_img), bias, out, N, overflow_flag);
+  kern<<<grid, SAT_THREADS, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, 0, 0, group, M,
+                                       reinterpret_cast<const uint4*>(w_img), bias, out, N, overflow_flag, 512, nullptr, nullptr, 1);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }
 
 // y[M, N] = act(x[M, K] (ld ldx, x >= 0) . W + bias + pos[M, 3] . Wp): dense layer on the tensor cores, N in column blocks of NB
-template <int K, int NB>
+template <int K>
 static int launch_linear_tc_t(const float* x, int ldx, int M, const float* w_img, const float* bias, int N, const float* pos,
                               const float* Wp, bool relu, float* y, int sms, int32_t* overflow_flag, cudaStream_t s) {
-  const size_t smem = sat_smem_bytes<NB>();
-  auto kern = sa_edge_tc_kernel<K, NB, true, true>;
+  constexpr int NB = 128;
+  const size_t smem = sat_smem_bytes<NB>(0, 3);
+  auto kern = sa_edge_tc_kernel<K, NB, true, true, K, 3, false, false>;
   T2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblocks = N / NB, tiles = (M + SAT_ROWS - 1) / SAT_ROWS;
   dim3 grid(std::max(1, std::min(tiles, sms / nblocks)), nblocks);
@@ -604,11 +627,11 @@ int launch_linear_tc(const float* x, int ldx, int M, int K, const float* w_img, 
                      const float* Wp, bool relu, float* y, int sms, int32_t* overflow_flag, cudaStream_t s) {
   if (M <= 0) return T2P_OK;
   T2P_REQUIRE(linear_tc_supported(K, N), T2P_ERR_UNSUPPORTED, "linear (tensor cores): K=%d N=%d", K, N);
-  if (K == 64) return launch_linear_tc_t<64, 128>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
-  if (K == 128) return launch_linear_tc_t<128, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
-  if (K == 256) return launch_linear_tc_t<256, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
-  if (K == 1024) return launch_linear_tc_t<1024, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
-  return launch_linear_tc_t<512, 256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 64) return launch_linear_tc_t<64>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 128) return launch_linear_tc_t<128>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 256) return launch_linear_tc_t<256>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  if (K == 1024) return launch_linear_tc_t<1024>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
+  return launch_linear_tc_t<512>(x, ldx, M, w_img, bias, N, pos, Wp, relu, y, sms, overflow_flag, s);
 }
 
 }  // namespace t2p

@@ -100,8 +100,10 @@ def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = Tru
         if (k, n) in ((32, 64), (128, 128), (256, 256)):
             blob_w = np.concatenate(bb.chunks)[d.sa_l2[l].w_off: d.sa_l2[l].w_off + k * n].astype(np.float64).reshape(k, n)
             if fits_fp16_split(blob_w, SA_TC_WSCALE):  # else: the exact-fp32 kernel serves this layer
-                if k == 32:      # K padded to one 64-wide chunk with zero rows
-                    img = _sa_tc_images(np.vstack([blob_w, np.zeros((32, n))]))
+                if k == 32:      # K padded to one 64-wide chunk, the column block to 128 output channels (zeros)
+                    pad = np.zeros((64, 128))
+                    pad[:32, :64] = blob_w
+                    img = _sa_tc_images(pad)
                 elif k == 256:   # two 128-column blocks (one CTA each), every block with its four K chunks
                     img = np.concatenate([_sa_tc_images(blob_w[:, j: j + 128]) for j in (0, 128)])
                 else:
@@ -109,10 +111,10 @@ def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = Tru
                 d.sa_l2_tc_off[l] = bb.add_raw_u32(img)
     k, n = d.ga_l2.k, d.ga_l2.n
     d.ga_l2_tc_off = -1
-    if k == 512 and n % 256 == 0:
+    if k == 512 and n % 128 == 0:
         blob_w = np.concatenate(bb.chunks)[d.ga_l2.w_off: d.ga_l2.w_off + k * n].astype(np.float64).reshape(k, n)
         if fits_fp16_split(blob_w, SA_TC_WSCALE):
-            d.ga_l2_tc_off = bb.add_raw_u32(np.concatenate([_sa_tc_images(blob_w[:, j: j + 256]) for j in range(0, n, 256)]))
+            d.ga_l2_tc_off = bb.add_raw_u32(np.concatenate([_sa_tc_images(blob_w[:, j: j + 128]) for j in range(0, n, 128)]))
     # x part of the dense layers (the last 3 rows of sa / ga first layers multiply pos and stay fp32): (layer, K of the x part, N)
     dense = [(d.sa_l1[1], 64, 128), (d.sa_l1[2], 128, 256), (d.ga_l1, 256, 512), (d.lin1, 1024, 512), (d.lin2, 512, 256)]
     for i in range(6):
@@ -123,8 +125,7 @@ def pack_pointnet2(bb: BlobBuilder, sd, prefix: str, self_loop_quirk: bool = Tru
             continue
         w = flat[lin.w_off: lin.w_off + lin.k * lin.n].astype(np.float64).reshape(lin.k, lin.n)[:kx]
         if fits_fp16_split(w, SA_TC_WSCALE):
-            nb = 128 if n == 128 else 256
-            d.dense_tc_off[i] = bb.add_raw_u32(np.concatenate([_sa_tc_images(w[:, j: j + nb]) for j in range(0, n, nb)]))
+            d.dense_tc_off[i] = bb.add_raw_u32(np.concatenate([_sa_tc_images(w[:, j: j + 128]) for j in range(0, n, 128)]))
     return d
 
 

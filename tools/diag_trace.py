@@ -24,13 +24,17 @@ t = np.array(buf, dtype=np.int64).reshape(16, 256)
 names = {0: "B0 builder got free table", 1: "B1 table published", 2: "M2 mma sees table", 3: "M3 mma has accumulator", 4: "M4 mma sees full stage",
          5: "M5 mma committed", 6: "P6 producer sees table", 7: "P7 producer has stage", 8: "P8 producer filled", 9: "P9 producer arrived",
          10: "E10 epi sees table", 11: "E11 epi sees accumulator", 12: "E12 epi done"}
-for lo, hi, what in ((60, 160, "SA3 (256 -> 256, column block 0)"), (185, 250, "SA2 (128 -> 128)")):
+for lo, hi, what in ((30, 250, os.environ.get("T2P_TRACE_WHAT", "traced instantiation")),):
     print("==", what, "items", lo, hi)
     seg = t[:, lo:hi]
     for ev in range(13):
-        per = np.diff(seg[ev]).astype(np.float64)
-        print(f"  {names[ev]:32s} period between items: median {np.median(per):8.0f} cycles, mean {per.mean():8.0f}")
-    chain = [(0, 1), (1, 6), (6, 7), (7, 8), (8, 9), (9, 4), (4, 5), (5, 11), (11, 12), (1, 12)]
+        col = seg[ev][seg[ev] != 0]
+        per = np.diff(col).astype(np.float64)
+        if per.size:
+            print(f"  {names[ev]:32s} period between recorded items: median {np.median(per):8.0f} cycles, mean {per.mean():8.0f}")
+    chain = [(0, 1), (1, 6), (6, 7), (7, 8), (8, 9), (9, 4), (4, 5), (5, 11), (10, 11), (11, 12), (1, 12)]
     for a, b in chain:
-        d = (seg[b] - seg[a]).astype(np.float64)
-        print(f"  {names[a][:3]} -> {names[b][:3]}: median {np.median(d):8.0f}  mean {d.mean():8.0f}  max {d.max():8.0f}")
+        ok = (seg[a] != 0) & (seg[b] != 0)
+        d = (seg[b] - seg[a])[ok].astype(np.float64)
+        if d.size:
+            print(f"  {names[a][:3]} -> {names[b][:3]}: median {np.median(d):8.0f}  mean {d.mean():8.0f}  max {d.max():8.0f}")

@@ -432,7 +432,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
                                   fmaxf(t1.x - s1.x, 0.f), fmaxf(t1.y - s1.y, 0.f), fmaxf(t1.z - s1.z, 0.f), fmaxf(t1.w - s1.w, 0.f)};
               uint32_t h[4], l[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) amax = a[j] <= amax ? amax : a[j];  // NaN sticks (the comparison is false)
+              for (int j = 0; j < 8; ++j) amax = fmaxf(amax, a[j]);  // (a >= 0 after the ReLU; one instruction per value)
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const __half2 hh = __floats2half2_rn(a[2 * j], a[2 * j + 1]);
@@ -489,7 +489,7 @@ sa_edge_tc_kernel(const float* __restrict__ T, const float* __restrict__ S, cons
         mbar_wait(&bars->tmem_full[acc], (uint32_t)((nv >> 1) & 1));
         tc_fence_after_sync();
         for (int cc = eh; cc < SAT_ROWS / 32; cc += NEH) {
-          if (cc * 32 >= rw->n_valid) break;  // warp-uniform: no edge in this group
+          if (cc * 32 >= rw->n_valid || n_off + quad * 32 >= ldo) break;  // warp-uniform: no edge in this group / padded channels only
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * SAT_ROWS + cc * 32, v);
           int rsv[32];  // the centres (output rows) of these 32 edges: the same for every thread

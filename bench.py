@@ -35,10 +35,11 @@ DB_1GPU = 10000
 DB_PER_GPU_MULTI = 12500
 MIN_TIMED_S = 0.3  # the K-step region is repeated until at least this much time has been measured; the median region is reported
 N_DB_COPIES = 32  # rotate DB copies (32 x 10 MB > 126 MB L2) so that every step streams its DB from HBM
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/r01_online_full.txt,
-# same command line, N = 1): the scan streams the DB once (10.33 MB vs 10.32 MB algorithmic); the LSTM reads its weights + table
-NCU_TRAFFIC = {"topk": 10332672 + 1727744, "lstm": 2510080}
-TRAFFIC_SOURCE = ("constant from the committed `ncu --set full` capture of this command line (profiles/r01_online_full.txt), per launch; "
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/r02_online_full.txt,
+# same command line, N = 1): the scan streams the DB once (10.34 MB vs 10.32 MB algorithmic) + the selects' candidate rows
+# (0.77 + 0.06 MB); the LSTM reads its weights + table
+NCU_TRAFFIC = {"topk": 10335744 + 773888 + 57856, "lstm": 2510848}
+TRAFFIC_SOURCE = ("constant from the committed `ncu --set full` capture of this command line (profiles/r02_online_full.txt), per launch; "
                   "NOT observed by this run (a run under ncu is never a bench value)")
 
 
@@ -48,8 +49,11 @@ def load_dsmem_peak():
     p = os.path.join(ROOT, "profiles", "r02_dsmem_bench.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(peak=float(d["peak_st_async_b_per_clk"]), src="measured (tools/dsmem_bench.cu -> profiles/r02_dsmem_bench.json: "
-                    f"best st.async.v4 figure over slice sizes / cluster counts on {d.get('gpu', 'B200')})")
+        # lstm_tc_kernel ships h with bulk DSMEM copies (cp.async.bulk.shared::cluster.shared::cta): its peak is the best bulk
+        # figure of the micro-benchmark (the st.async.v4 mechanism of round 1 tops out at peak_st_async_b_per_clk)
+        return dict(peak=float(d["peak_bulk_b_per_clk"]), src="measured (tools/dsmem_bench.cu -> profiles/r02_dsmem_bench.json: "
+                    f"best cp.async.bulk figure over slice sizes / cluster counts on {d.get('gpu', 'B200')}; st.async.v4 tops out at "
+                    f"{d['peak_st_async_b_per_clk']} B/clk)")
     return dict(peak=17.0, src="UNMEASURED fallback: B300_MICROARCH.md quotes 17 B/clk bidirectional for the same SM design")
 
 
@@ -434,9 +438,9 @@ def main_b200(args):
            "d2h_bytes_per_step": eng.d2h_bytes() * world, "steps": n_e2e, "reps": e_reps, "timed_region_s": float(e_regions.sum()),
            "ms_per_step": dt / n_e2e * 1e3,
            "call": call + " -> (idx, scores) numpy per rank: raw text staged into pinned memory, 1 H2D copy, " +
-                   ("CUDA graph of the 5 kernels (device tokeniser first)" if world == 1 else
-                    ("CUDA graph of 5 kernels + 2 peer pushes/waits over NVLink IPC memory + merge" if args.exchange == "p2p" else
-                     "5 kernels + 2 NCCL all-gathers + merge")) + ", 1 D2H copy, synchronise"}
+                   ("CUDA graph of the 6 kernels (device tokeniser first)" if world == 1 else
+                    ("CUDA graph of 6 kernels + 2 peer pushes/waits over NVLink IPC memory + merge" if args.exchange == "p2p" else
+                     "6 kernels + 2 NCCL all-gathers + merge")) + ", 1 D2H copy, synchronise"}
 
     # ---- parity guard against the oracle over the FULL DB (every rank checks its own queries) ---------------------------
     import oracle
@@ -513,7 +517,8 @@ def main_b200(args):
     n_local = hi - lo
     topk_bytes = n_local * EMBED * 4 + q_per_step * EMBED * 4 + q_per_step * TOPK * 16
     lstm_flops = 2 * mean_len * 2 * B_QUERIES * (EMBED * 4 * EMBED * 2)  # 2 dirs x T x 2*B*(hh + ih)
-    roof_topk = {"kernel": "retrieve_scan_tc_kernel+retrieve_select_kernel" + ("" if world == 1 else " (+2 all-gathers, merge)"),
+    roof_topk = {"kernel": "retrieve_scan_tc_kernel+retrieve_select_warp_kernel(+retrieve_select_kernel for uncertified queries)" +
+                           ("" if world == 1 else " (+2 all-gathers, merge)"),
                  "bound": "hbm", "achieved": topk_bytes / (topk_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                  "traffic": NCU_TRAFFIC["topk"] if world == 1 else None, "ms": topk_ms, "algorithmic_bytes": topk_bytes,
                  "traffic_source": TRAFFIC_SOURCE}
@@ -522,9 +527,10 @@ def main_b200(args):
                  "achieved": lstm_flops / (lstm_ms * 1e-3) / 1e12, "peak": peaks["bf16"], "unit": "TFLOP/s",
                  "traffic": NCU_TRAFFIC["lstm"], "traffic_source": TRAFFIC_SOURCE, "ms": lstm_ms, "algorithmic_flops": lstm_flops,
                  "note": "~50 strictly dependent steps of a [64,256]x[256,1024] product per direction on tcgen05 (fp16 hi/lo split, "
-                         "3 products, fp32 accumulate; W_hh resident in tensor memory); bound by the per-step h exchange over the "
-                         "SM-to-SM network, not by the tensor pipe: see roofline_network (the binding resource); reported here "
-                         "against the bf16 tensor peak as the contract asks"}
+                         "3 products, fp32 accumulate; W_hh resident in tensor memory, h exchanged with bulk DSMEM copies); a step is a "
+                         "dependent chain MMA -> cell update -> SM-to-SM copy, so the kernel is latency-bound per step (ncu: tensor pipe "
+                         "40 % active on the 16 SMs in use); reported against the bf16 tensor peak as the contract asks, "
+                         "roofline_network gives the SM-to-SM traffic against its measured peak"}
     roof_lstm["frac"] = roof_lstm["achieved"] / peaks["bf16"]
     # the resource that actually binds the recurrence: the SM-to-SM network.  Every CTA of a cluster sends
     # 7/8 of its 32-unit slice of h (fp16 hi + lo) of every sequence to its 7 peers and receives as much, every step.

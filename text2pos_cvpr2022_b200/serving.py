@@ -83,7 +83,7 @@ class _Slot:
 
 
 class OnlineRetrievalEngine:
-    KERNELS_PER_STEP = 5  # tokenize, lstm_tc, lstm_finalize, retrieve_scan_tc, retrieve_select
+    KERNELS_PER_STEP = 6  # tokenize, lstm_tc, lstm_finalize, retrieve_scan_tc, retrieve_select_warp, retrieve_select (flagged only)
 
     def __init__(self, model, db: torch.Tensor, k: int = 10, max_batch: int = 64, max_tokens: int = 64,
                  idx_base: int = 0, cell_ids: Optional[Sequence[str]] = None, depth: int = 1, max_text_bytes: int = 1024,

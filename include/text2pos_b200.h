@@ -86,6 +86,7 @@ int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, 
 int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
                          const float* d_db_norm2_max, int flags, double* d_out_scores, int64_t* d_out_idx,
                          int32_t* d_stats, void* d_ws, size_t ws_bytes, t2p_stream stream);
+
 int t2p_db_row_norm2_max(const float* d_db, int N, int D, float* d_out, t2p_stream stream);
 /* merge R per-shard lists [R,B,k_in] (e.g. after an all-gather) into [B,k_out], same ordering rule */
 int t2p_topk_merge(const double* d_scores, const int64_t* d_idx, int R, int B, int k_in, int k_out,
@@ -270,6 +271,13 @@ int t2p_tokenize_device(const t2p_vocab* v, const void* d_stage, int n_texts, in
 int t2p_serving_submit(const char* texts, size_t total_bytes, int n_texts, void* h_stage, size_t stage_capacity, void* d_stage,
                        void* graph_exec, const void* d_out, void* h_out, size_t out_bytes, void* event, t2p_stream stream,
                        size_t* used_bytes, int* all_ascii);
+
+/* Device-resident serving loop: launches n captured steps back to back, step i = graph_execs[i] (cudaGraphExec_t) on
+ * streams[i], with no interpreter between the launches (a Python-level replay costs ~25 us per step, more than the GPU needs
+ * for one).  The inputs of the captured steps (staged text, DB) are already resident; nothing is copied.  fork_join != 0: the
+ * distinct streams first wait for the work enqueued on `origin` so far and `origin` waits for all of them at the end (events
+ * recorded on `origin` around the call then bracket the whole region). */
+int t2p_serving_replay_many(void* const* graph_execs, const t2p_stream* streams, int n, t2p_stream origin, int fork_join);
 
 size_t t2p_lstm_encode_workspace(int B, int H);
 /* d_tokens [B,T] int32 (row b valid for t < d_lengths[b]), 1 <= lengths <= T.  d_out [B,H] =

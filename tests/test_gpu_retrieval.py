@@ -110,6 +110,11 @@ def test_tensor_core_path_equals_float64_oracle(B, N, D, k):
     if N >= 1000:  # well separated synthetic scores: the TF32 candidates certify, no rescan needed
         assert st[1] == 0, st
     _check_flags(db, q, k, _lib.RETRIEVE_FORCE_GENERIC)
+    # serving geometry: few scan CTAs, each streaming many DB tiles against its resident query tile
+    for cap in (40, 8):
+        st = _check_flags(db, q, k, _lib.retrieve_max_ctas(cap), idx_base=1000 * cap)
+        if N >= 1000:
+            assert st[1] == 0, st
 
 
 def test_tensor_core_forced_rescan_is_exact():

@@ -149,6 +149,7 @@ PROTOTYPES = {
     "t2p_stage_texts": (_I, [C.c_char_p, _SZ, _I, _P, _SZ, _P, _P, C.POINTER(_SZ), C.POINTER(_I)]),
     "t2p_tokenize_device": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "t2p_serving_submit": (_I, [C.c_char_p, _SZ, _I, _P, _SZ, _P, _P, _P, _P, _SZ, _P, _P, C.POINTER(_SZ), C.POINTER(_I)]),
+    "t2p_serving_replay_many": (_I, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I, _P, _I]),
     "t2p_lstm_encode_workspace": (_SZ, [_I, _I]),
     "t2p_lstm_encode": (_I, [_P, C.POINTER(LstmDesc), _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "t2p_superglue_workspace": (_SZ, [_I, _I, _I, _I]),

@@ -57,7 +57,7 @@ int launch_knn_cells(const float* e, const int32_t* cell_offsets, int n_cells, i
 // tensor-core (tcgen05 + TMA) retrieval path, csrc/retrieval_tc.cu
 struct TcPlan {
   bool ok;
-  int KP, NC, tile_n, tiles, G, tiles_per_cta, nb_bits, qtiles, dup, qstream, nsrc, q_pitch, st_pitch, stages;
+  int KP, NC, tile_n, tiles, G, tiles_per_cta, nb_bits, qtiles, dup, qstream, nsrc, q_pitch, st_pitch, stages, a_tmem, slack, parts;
   size_t scan_smem, sel_smem;
 };
 TcPlan tc_plan(int B, int N, int D, int k, int sms);

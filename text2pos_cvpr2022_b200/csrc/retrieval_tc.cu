@@ -18,7 +18,9 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "kernels.h"
 #include "sm100.cuh"
@@ -32,9 +34,14 @@ constexpr int TC_QM = 128;          // queries per tile (UMMA M)
 constexpr int TC_TILE_MAX = 128;    // DB rows per tile (UMMA N), multiple of 16
 constexpr int TC_STAGES = 4;
 constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 32 floats
-constexpr int TC_THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int TC_EPI_WARPS = 8;     // at most two per TMEM lane quadrant (they take alternate 16-column chunks of every tile)
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
 constexpr int TC_MAX_TILES_PER_CTA = 16;
-constexpr int TC_TMEM_COLS = 256;   // 2 accumulators x 128 columns
+constexpr int TC_TMEM_COLS = 512;   // [0, 256): 2 accumulators x 128 columns; [256, 256 + D): the query tile (A operand)
+constexpr int TC_Q_COL = 256;
+constexpr int TC_EPI_DEFAULT = 4;
+constexpr int TC_CAND_CAP = 32;     // candidate keys a lane may buffer between two merges into its sorted list
+constexpr int TC_CAND_BYTES = TC_EPI_WARPS * TC_CAND_CAP * 32 * 4;  // epilogue warps x CAP x 32 lanes x u32 = 32 KB
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_CAND_MAX = 64;
 // |tf32 score - exact score| <= TC_EPS * |q| * |d|: both operands lose < 2^-10 relative (13 mantissa bits dropped),
@@ -52,6 +59,23 @@ __device__ __forceinline__ float key_upper_score(uint32_t key, uint32_t low_mask
   uint32_t u = key | low_mask;
   u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
   return __uint_as_float(u);
+}
+
+// smallest score whose key could exceed `key` (low bits cleared): key(v) > key  =>  v >= key_lower_score(key)
+__device__ __forceinline__ float key_lower_score(uint32_t key, uint32_t low_mask) {
+  uint32_t u = key & ~low_mask;
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  const float t = __uint_as_float(u);
+  return (t == t) ? t : -INFINITY;  // a NaN bit pattern (keys of huge negative scores) must not reject everything
+}
+
+// sorted (descending) register list: insert x with a depth-2 network -- L'[i] = max(L[i], min(L[i-1], x)) -- instead of a
+// 16-deep dependent min/max chain (x = 0 is a no-op: keys are >= 0)
+template <int KP>
+__device__ __forceinline__ void topk_insert(uint32_t (&L)[KP], uint32_t x) {
+#pragma unroll
+  for (int i = KP - 1; i >= 1; --i) L[i] = max(L[i], min(L[i - 1], x));
+  L[0] = max(L[0], x);
 }
 
 // ---- max squared row norm of the DB (input of the certification bound) -------------------------------------
@@ -73,6 +97,39 @@ __global__ void __launch_bounds__(256) row_norm2_max_kernel(const float* __restr
 }
 
 // ---- scan ----------------------------------------------------------------------------------------------
+#ifdef T2P_SCAN_TRACE  // tools/make_scan_trace.py: %globaltimer stamps of CTA (0, 0), read back with t2p_debug_scan_trace
+__device__ unsigned long long scan_trace[128];
+#define STR(i)                                                          \
+  do {                                                                  \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < 128) {              \
+      unsigned long long t_;                                            \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));            \
+      scan_trace[(i)] = t_;                                             \
+    }                                                                   \
+  } while (0)
+#else
+#define STR(i) do {} while (0)
+#endif
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32 (A: one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void scan_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 constexpr int TC_MAX_STAGES = 12;
 
 struct ScanSmem {
@@ -98,37 +155,44 @@ struct ScanParams {
   int qstream;     // B > 128 and one DB tile per CTA: the DB tile stays resident (q_pitch = its chunk pitch) and the QUERY
                    // tiles stream through the ring (st_pitch = 16 KB); one key list per (query, CTA) and query tile
   int qtiles;
+  int a_tmem;      // not qstream: the query tile lives in TENSOR memory (A operand of the TS form; columns [256, 256 + D)), written
+                   // once by the epilogue warps -- all of shared memory is the DB ring (the 128 KB tile left room for 2 stages)
+  int slack;       // bytes after the ring the UMMA may read past a short resident tile (SS forms only)
+  int epi_warps;   // 4 or 8 epilogue warps (1 or 2 key lists per (query, CTA, half))
+  int debug;       // T2P_SCAN_DEBUG knock-outs (tools only; results are wrong): 1 = no UMMAs, 2 = no column scan
 };
 
 template <int KP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                        const ScanParams p, uint32_t* __restrict__ part_keys) {
+                        const ScanParams p, const float* __restrict__ q_rows, uint32_t* __restrict__ part_keys) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nch = p.D >> 5;  // 128-byte chunks along K
   uint8_t* q_smem = base;
   uint8_t* st_smem = base + (size_t)nch * p.q_pitch;
   // the UMMA reads 128 rows (16 KB) from every query chunk whatever q_pitch is: 16 KB of slack follow the stages
-  ScanSmem* sm = reinterpret_cast<ScanSmem*>(st_smem + (size_t)p.stages * p.st_pitch + 16384);
+  uint32_t* cand_smem = reinterpret_cast<uint32_t*>(st_smem + (size_t)p.stages * p.st_pitch + p.slack);
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(st_smem + (size_t)p.stages * p.st_pitch + p.slack + TC_CAND_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x;
   const int q0 = blockIdx.y * TC_QM;
+  if (threadIdx.x == 0) STR(0);
   const int tile_n = p.tile_n;
   const int tiles = (p.N + tile_n - 1) / tile_n;
   // iterations of the pipeline: DB tiles of this CTA (query tile resident) or query tiles (qstream: DB tile resident)
   const int my_tiles = p.qstream ? p.qtiles : (tiles - c + G - 1) / G;  // host guarantees c < tiles
 
   if (threadIdx.x == 0) {
-    mbar_init(&sm->q_full, 1);
+    mbar_init(&sm->q_full, p.a_tmem ? p.epi_warps : 1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&sm->full[s], 1);
       mbar_init(&sm->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm->tmem_full[a], 1);
-      mbar_init(&sm->tmem_empty[a], 128);
+      mbar_init(&sm->tmem_empty[a], p.epi_warps);
     }
     mbar_fence_init();
   }
@@ -137,7 +201,12 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = sm->tmem_slot;
+  if (threadIdx.x == 0) STR(1);
 
+  auto WAIT = [&](uint64_t* bar, uint32_t parity) {
+    if (p.debug & 4) mbar_wait(bar, parity);
+    else mbar_wait_spin(bar, parity);
+  };
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -151,23 +220,25 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int kc = 0; kc < nch; ++kc) tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_db, kc * 32, c * tile_n, &sm->q_full);
         for (int qt = 0; qt < my_tiles; ++qt) {
           for (int kc = 0; kc < nch; ++kc) {
-            mbar_wait(&sm->empty[stage], ph ^ 1);
+            WAIT(&sm->empty[stage], ph ^ 1);
             mbar_expect_tx(&sm->full[stage], (uint32_t)(p.q_box_rows * 128));
             tma_load_2d(st_smem + (size_t)stage * p.st_pitch, &tmap_q, kc * 32, qt * TC_QM, &sm->full[stage]);
             if (++stage == p.stages) { stage = 0; ph ^= 1; }
           }
         }
       } else {
-        const int q_copies = p.dup ? 2 : 1;
-        mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_copies * p.q_box_rows * 128));
-        for (int kc = 0; kc < nch; ++kc) {
-          tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_q, kc * 32, q0, &sm->q_full);
-          if (p.dup) tma_load_2d(q_smem + (size_t)kc * p.q_pitch + 64 * 128, &tmap_q, kc * 32, q0, &sm->q_full);
+        if (!p.a_tmem) {
+          const int q_copies = p.dup ? 2 : 1;
+          mbar_expect_tx(&sm->q_full, (uint32_t)(nch * q_copies * p.q_box_rows * 128));
+          for (int kc = 0; kc < nch; ++kc) {
+            tma_load_2d(q_smem + (size_t)kc * p.q_pitch, &tmap_q, kc * 32, q0, &sm->q_full);
+            if (p.dup) tma_load_2d(q_smem + (size_t)kc * p.q_pitch + 64 * 128, &tmap_q, kc * 32, q0, &sm->q_full);
+          }
         }
         for (int lt = 0; lt < my_tiles; ++lt) {
           const int row0 = (c + lt * G) * tile_n;
           for (int kc = 0; kc < nch; ++kc) {
-            mbar_wait(&sm->empty[stage], ph ^ 1);
+            WAIT(&sm->empty[stage], ph ^ 1);
             mbar_expect_tx(&sm->full[stage], (uint32_t)(p.db_box_rows * 128));
             tma_load_2d(st_smem + (size_t)stage * p.st_pitch, &tmap_db, kc * 32, row0, &sm->full[stage]);
             if (++stage == p.stages) { stage = 0; ph ^= 1; }
@@ -181,46 +252,98 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(TC_QM, tile_n);
       const uint32_t q_addr = smem_u32(q_smem), st_addr = smem_u32(st_smem);
-      mbar_wait(&sm->q_full, 0);
+      WAIT(&sm->q_full, 0);
+      STR(3);
       int stage = 0;
       uint32_t ph = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
         const int acc = lt & 1;
-        mbar_wait(&sm->tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        WAIT(&sm->tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * TC_TILE_MAX;
         for (int kc = 0; kc < nch; ++kc) {
-          mbar_wait(&sm->full[stage], ph);
+          WAIT(&sm->full[stage], ph);
           tc_fence_after_sync();
           // A = queries (M = 128 TMEM lanes), B = DB rows (N = tile_n columns); which of them is resident depends on the mode
           const uint64_t res_desc = umma_desc_sw128_kmajor(q_addr + kc * p.q_pitch);
           const uint64_t str_desc = umma_desc_sw128_kmajor(st_addr + stage * p.st_pitch);
           const uint64_t a_desc = p.qstream ? str_desc : res_desc;
           const uint64_t b_desc = p.qstream ? res_desc : str_desc;
+          if (p.debug & 1) {
+          } else if (p.a_tmem) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
-            umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks)  // A: 8 tensor-memory columns per instruction
+              umma_tf32_ts(d_tmem, tmem_base + TC_Q_COL + kc * 32 + ks * 8, str_desc + 2 * ks, idesc, (kc | ks) != 0);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
+              umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+          }
           umma_commit(&sm->empty[stage]);
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
         umma_commit(&sm->tmem_full[acc]);
+        STR(8 + lt);
       }
     }
     __syncwarp();
   } else {
     // ===== epilogue: TMEM lane = query, columns = DB rows of the tile =====
+    // A lane keeps the KP best keys of its query as a sorted register list.  Scores are first filtered against the lane's
+    // threshold (a float lower bound of its KP-th key; one compare per score) and the survivors are appended, as keys, to the
+    // lane's column of a shared-memory buffer; when some lane's buffer runs full the warp merges the buffers into the lists
+    // (max-over-lanes rounds of the depth-2 insertion network) and refreshes the thresholds.  The warp-wide insertion per
+    // column of the first version ran for ~90 % of the columns (32 queries share the branch) and was a 16-deep dependent chain.
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     const int tl = quad * 32 + lane;
     const int half = p.dup ? (tl >> 6) : 0;
+    const int sub = (warp - 2) >> 2;  // which of the warps of the quadrant
+    const int subs = p.epi_warps >> 2;
     const uint32_t low_mask = (1u << p.nb_bits) - 1u;
+    if (p.a_tmem) {
+      // the query tile goes to tensor memory once: TMEM lane = query row (rows 64.. mirror 0..63 in dup mode), column = channel
+      // the warps of a quadrant take alternate 32-channel blocks
+      const int qr = q0 + (p.dup ? (tl & 63) : tl);
+      const float4* src = reinterpret_cast<const float4*>(q_rows + (size_t)min(qr, p.B - 1) * p.D);
+        for (int c0 = 32 * sub; c0 < p.D; c0 += 32 * subs) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = qr < p.B ? __ldg(src + (c0 >> 2) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * i] = __float_as_uint(x.x); v[4 * i + 1] = __float_as_uint(x.y);
+            v[4 * i + 2] = __float_as_uint(x.z); v[4 * i + 3] = __float_as_uint(x.w);
+          }
+          scan_tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + TC_Q_COL + c0, v);
+        }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->q_full);
+      if (warp == 2 && lane == 0) STR(2);
+    }
+    // the lane's column of the warp's candidate buffer, as a shared-space address (slot r at +128 r bytes)
+    const uint32_t buf = smem_u32(cand_smem + (warp - 2) * (TC_CAND_CAP * 32) + lane);
     uint32_t L[KP];
 #pragma unroll
     for (int i = 0; i < KP; ++i) L[i] = 0u;
+    float thr = -INFINITY;
+    uint32_t cnt = 0;
+    auto merge = [&]() {
+      const uint32_t rounds = __reduce_max_sync(0xffffffffu, cnt);
+      for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t x;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(buf + (r << 7)));
+        topk_insert<KP>(L, r < cnt ? x : 0u);
+      }
+      cnt = 0;
+      if (L[KP - 1] != 0u) thr = key_lower_score(L[KP - 1], low_mask);
+    };
     const int n16 = tile_n >> 4;
     const int ch_begin = (p.dup && half) ? ((n16 + 1) >> 1) : 0;
     const int ch_end = (p.dup && !half) ? ((n16 + 1) >> 1) : n16;
-    const int nsrc = p.dup ? 2 * G : G;
-    const int src = p.dup ? 2 * c + half : c;
+    const int parts = (p.dup ? 2 : 1) * subs;  // key lists per (query, CTA)
+    const int nsrc = parts * G;
+    const int src = parts * c + half * subs + sub;
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int acc = lt & 1;
       // qstream: iteration lt is query tile lt against the CTA's single DB tile; otherwise DB tile lt against query tile blockIdx.y
@@ -229,32 +352,69 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const bool warp_active = (qbase + (p.dup ? ((quad & 1) * 32) : quad * 32)) < p.B;
       const int row0 = p.qstream ? c * tile_n : (c + lt * G) * tile_n;
       const uint32_t local0 = p.qstream ? 0u : (uint32_t)(lt * TC_TILE_MAX);
+      const int ncols = min(tile_n, p.N - row0);  // valid columns of this tile (the rows TMA zero-fills must not become candidates)
       mbar_wait(&sm->tmem_full[acc], (lt >> 1) & 1);
+      if (warp == 2 && lane == 0) STR(40 + lt);
       tc_fence_after_sync();
-      if (warp_active) {
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_TILE_MAX + ch * 16, v);
-          tmem_ld_wait();
+      if (warp_active && ch_begin + sub < ch_end && !(p.debug & 2)) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_TILE_MAX;
+        // branch-free filter: the key of every score is written to the lane's next free slot, the slot is only kept (cnt
+        // advances) if the score passes the threshold.  Four columns per group: their slots are cnt + (prefix of the hit
+        // bits), so the dependent chain through cnt is one add per four columns.
+        auto scan16_impl = [&](const uint32_t (&v)[16], int ch, auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
+          const uint32_t key0 = low_mask - (local0 + (uint32_t)(ch * 16));
+          const int left = ncols - ch * 16;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = ch * 16 + j;
-            const bool ok = row0 + col < p.N;
-            uint32_t x = ok ? score_to_key(__uint_as_float(v[j]), low_mask, local0 + (uint32_t)col) : 0u;
-            if (__any_sync(0xffffffffu, x > L[KP - 1])) {
+          for (int g = 0; g < 4; ++g) {
+            uint32_t key[4], hit[4];
 #pragma unroll
-              for (int i = 0; i < KP; ++i) {
-                const uint32_t hi = max(L[i], x);
-                x = min(L[i], x);
-                L[i] = hi;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * g + i;
+              uint32_t u = v[j];
+              u ^= (uint32_t)((int32_t)u >> 31) | 0x80000000u;  // order-preserving bits (score_to_key)
+              key[i] = (u & ~low_mask) | (key0 - (uint32_t)j);
+              hit[i] = (__uint_as_float(v[j]) >= thr && (FULL || j < left)) ? 1u : 0u;
             }
+            const uint32_t s1 = hit[0], s2 = hit[0] + hit[1], s3 = s2 + hit[2], s4 = s3 + hit[3];
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf + (cnt << 7)), "r"(key[0]));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf + ((cnt + s1) << 7)), "r"(key[1]));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf + ((cnt + s2) << 7)), "r"(key[2]));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf + ((cnt + s3) << 7)), "r"(key[3]));
+            cnt += s4;
           }
+          if (__any_sync(0xffffffffu, cnt > (uint32_t)(TC_CAND_CAP - 16))) merge();
+        };
+        const bool full_tile = ncols == tile_n;  // every tile but the last one of the DB
+        auto scan16 = [&](const uint32_t (&v)[16], int ch) {
+          if (full_tile) scan16_impl(v, ch, std::true_type{});
+          else scan16_impl(v, ch, std::false_type{});
+        };
+        // the TMEM load of the warp's next chunk is in flight while the current one is filtered
+        uint32_t va[16], vb[16];
+        int ch = ch_begin + sub;
+        tmem_ld_32x16(t_addr + ch * 16, va);
+        tmem_ld_wait_on(va);
+        while (true) {
+          const bool more = ch + subs < ch_end;
+          if (more) tmem_ld_32x16(t_addr + (ch + subs) * 16, vb);
+          scan16(va, ch);
+          if (!more) break;
+          tmem_ld_wait_on(vb);
+          const bool more2 = ch + 2 * subs < ch_end;
+          if (more2) tmem_ld_32x16(t_addr + (ch + 2 * subs) * 16, va);
+          scan16(vb, ch + subs);
+          if (!more2) break;
+          tmem_ld_wait_on(va);
+          ch += 2 * subs;
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(&sm->tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->tmem_empty[acc]);
+      if (warp == 2 && lane == 0) STR(72 + lt);
       if (p.qstream || lt == my_tiles - 1) {  // the list of (query, CTA) is complete: write it (qstream: one per query tile)
+        if (warp_active) merge();
         if (qrow < p.B && warp_active) {
           uint4* dst = reinterpret_cast<uint4*>(part_keys + ((size_t)qrow * nsrc + src) * KP);
 #pragma unroll
@@ -262,13 +422,16 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
 #pragma unroll
         for (int i = 0; i < KP; ++i) L[i] = 0u;
+        thr = -INFINITY;
       }
     }
   }
+  if (warp == 2 && lane == 0) STR(4);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 0) STR(5);
 }
 
 // ---- select ----------------------------------------------------------------------------------------------
@@ -298,9 +461,9 @@ struct __align__(16) SelSmem {
 
 struct SelParams {
   int B, N, D;
-  int nsrc;    // key lists per query (CTAs of the scan, x2 in dup mode)
+  int nsrc;    // key lists per query (CTAs of the scan x parts)
   int G;       // CTAs of the scan (row decoding)
-  int dup;
+  int parts;   // key lists per (query, CTA): 2 epilogue warps per lane quadrant, x2 in dup mode
   int KP, NC, k, tile_n, nb_bits;
   int force_rescan;
   int64_t idx_base;
@@ -324,7 +487,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
   const double NINF = __longlong_as_double(0xfff0000000000000LL);
   auto row_of = [&](int pos, uint32_t key) -> int {
     const int src = pos / KP;
-    const int cta = p.dup ? (src >> 1) : src;
+    const int cta = src / p.parts;
     const uint32_t local = low_mask - (key & low_mask);
     return (cta + (int)(local >> 7) * p.G) * p.tile_n + (int)(local & 127u);
   };
@@ -703,7 +866,7 @@ retrieve_select_warp_kernel(const float* __restrict__ q, const float* __restrict
 
   auto row_of = [&](int pos, uint32_t key) -> int {
     const int src = pos / KP;
-    const int cta = p.dup ? (src >> 1) : src;
+    const int cta = src / p.parts;
     const uint32_t local = low_mask - (key & low_mask);
     return (cta + (int)(local >> 7) * p.G) * p.tile_n + (int)(local & 127u);
   };
@@ -842,6 +1005,13 @@ static int ceil_log2(int x) {
   return b;
 }
 
+// epilogue warps of the scan: 8 halve the latency of a scan, 4 cost fewer threads and half the key lists for the select
+// (T2P_SCAN_EPI overrides, for experiments)
+static int scan_epi_warps() {
+  static const int n = [] { const char* e = getenv("T2P_SCAN_EPI"); return (e && atoi(e) == 4) ? 4 : (e && atoi(e) == 8) ? 8 : TC_EPI_DEFAULT; }();
+  return n;
+}
+
 TcPlan tc_plan(int B, int N, int D, int k, int sms) {
   TcPlan p = {};
   p.ok = false;
@@ -850,30 +1020,40 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
   p.NC = k <= 16 ? 32 : 48;
   p.qtiles = (B + TC_QM - 1) / TC_QM;
   p.dup = B <= 64 ? 1 : 0;
-  // rows per tile: spread the DB over all SMs when it is small, 128-row tiles otherwise
-  int per_sm = (N + sms - 1) / sms;
-  p.tile_n = std::min(TC_TILE_MAX, std::max(16, (per_sm + 15) / 16 * 16));
-  p.tiles = (N + p.tile_n - 1) / p.tile_n;
-  p.G = std::min(p.tiles, sms);
-  p.tiles_per_cta = (p.tiles + p.G - 1) / p.G;
-  if (p.tiles_per_cta > TC_MAX_TILES_PER_CTA) {  // keep the index field of the keys small: more CTAs than SMs
+  // rows per tile: spread the DB over all SMs when it is small, 128-row tiles otherwise.  `sms` bounds the CTAs of the whole
+  // launch: with several query tiles (grid = G x qtiles) every query tile gets sms / qtiles CTAs, unless the DB is so small
+  // that one tile per CTA covers it (qstream below: grid = G, the query tiles stream through the CTA)
+  auto split = [&](int ctas) {
+    const int per_sm = (N + ctas - 1) / ctas;
+    p.tile_n = std::min(TC_TILE_MAX, std::max(16, (per_sm + 15) / 16 * 16));
+    p.tiles = (N + p.tile_n - 1) / p.tile_n;
+    p.G = std::min(p.tiles, ctas);
+    p.tiles_per_cta = (p.tiles + p.G - 1) / p.G;
+  };
+  split(sms);
+  if (p.qtiles > 1 && p.tiles_per_cta > 1) split(std::max(1, sms / p.qtiles));
+  if (p.tiles_per_cta > TC_MAX_TILES_PER_CTA) {  // keep the index field of the keys small: more CTAs than asked for
     p.tiles_per_cta = TC_MAX_TILES_PER_CTA;
     p.G = (p.tiles + TC_MAX_TILES_PER_CTA - 1) / TC_MAX_TILES_PER_CTA;
   }
-  p.nsrc = p.dup ? 2 * p.G : p.G;
+  p.parts = (p.dup ? 2 : 1) * (scan_epi_warps() / 4);
+  p.nsrc = p.parts * p.G;
   p.nb_bits = 7 + ceil_log2(p.tiles_per_cta);
   const int nch = D / 32;
   // several query tiles against a DB that gives every CTA one tile: keep the DB tile resident and stream the queries
   // (one launch wave, the DB is read once, no per-query-tile prologue)
   p.qstream = (p.qtiles > 1 && p.tiles_per_cta == 1) ? 1 : 0;
+  p.a_tmem = p.qstream ? 0 : 1;
   if (p.qstream) {
     p.q_pitch = (int)align_up((size_t)p.tile_n * 128, 1024);  // resident operand: the DB tile
     p.st_pitch = TC_QM * 128;                                  // streamed operand: one 128-query chunk
+    p.slack = 16384;  // the UMMA reads 128 rows from every chunk of the resident tile whatever its height
   } else {
-    p.q_pitch = (int)align_up((size_t)(p.dup ? 128 : std::min(TC_QM, B)) * 128, 1024);
+    p.q_pitch = 0;    // the query tile lives in tensor memory
     p.st_pitch = p.tile_n * 128;
+    p.slack = 0;
   }
-  const size_t fixed = 1024 + (size_t)nch * p.q_pitch + 16384 + sizeof(ScanSmem) + 64;
+  const size_t fixed = 1024 + (size_t)nch * p.q_pitch + p.slack + TC_CAND_BYTES + sizeof(ScanSmem) + 64;
   const size_t budget = 220 * 1024;
   if (fixed + 2 * (size_t)p.st_pitch > budget) return p;
   p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / p.st_pitch);
@@ -918,20 +1098,24 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
   sp.db_box_rows = std::min(p.tile_n, N);
   sp.q_pitch = p.q_pitch; sp.st_pitch = p.st_pitch; sp.stages = p.stages;
   sp.nb_bits = p.nb_bits; sp.dup = p.dup; sp.qstream = p.qstream; sp.qtiles = p.qtiles;
+  sp.a_tmem = p.a_tmem; sp.slack = p.slack;
+  static const int scan_debug = [] { const char* e = getenv("T2P_SCAN_DEBUG"); return e ? atoi(e) : 0; }();
+  sp.debug = scan_debug;
+  sp.epi_warps = scan_epi_warps();
   CUtensorMap tq, tdb;
   T2P_TRY(make_tmap_rows(&tq, d_q, B, D, sp.q_box_rows));
   T2P_TRY(make_tmap_rows(&tdb, d_db, N, D, sp.db_box_rows));
   dim3 grid(p.G, p.qstream ? 1 : p.qtiles);
   if (p.KP == 16) {
     T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
-    retrieve_scan_tc_kernel<16><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, sp, part);
+    retrieve_scan_tc_kernel<16><<<grid, 32 * (2 + scan_epi_warps()), p.scan_smem, s>>>(tq, tdb, sp, d_q, part);
   } else {
     T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
-    retrieve_scan_tc_kernel<32><<<grid, TC_THREADS, p.scan_smem, s>>>(tq, tdb, sp, part);
+    retrieve_scan_tc_kernel<32><<<grid, 32 * (2 + scan_epi_warps()), p.scan_smem, s>>>(tq, tdb, sp, d_q, part);
   }
   T2P_LAUNCH_CHECK();
   SelParams q;
-  q.B = B; q.N = N; q.D = D; q.nsrc = p.nsrc; q.G = p.G; q.dup = p.dup; q.KP = p.KP; q.NC = p.NC; q.k = k;
+  q.B = B; q.N = N; q.D = D; q.nsrc = p.nsrc; q.G = p.G; q.parts = p.parts; q.KP = p.KP; q.NC = p.NC; q.k = k;
   q.tile_n = p.tile_n; q.nb_bits = p.nb_bits; q.force_rescan = force_rescan; q.idx_base = idx_base;
   if (p.sel_smem > 48 * 1024)
     T2P_CUDA(cudaFuncSetAttribute(retrieve_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sel_smem));
@@ -953,3 +1137,9 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
 }
 
 }  // namespace t2p
+
+#ifdef T2P_SCAN_TRACE
+extern "C" int t2p_debug_scan_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, t2p::scan_trace, sizeof(t2p::scan_trace));
+}
+#endif

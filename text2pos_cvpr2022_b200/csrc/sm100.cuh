@@ -58,6 +58,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polling flavour (bounded as well) for single-thread roles on a latency-critical chain (an MMA issuer waiting for its operands):
+// nothing else wants the issue slots of that warp, and a parked thread wakes up later than a polling one notices.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1ll << 28)) __trap();
+  }
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -141,6 +150,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same, with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait (needed when
+// the load of the next chunk is issued before the current one is consumed)
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 
 }  // namespace sm100
 }  // namespace t2p

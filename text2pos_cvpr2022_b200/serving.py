@@ -43,6 +43,19 @@ def _native_submit(lib, descriptions, B, st, key, graph, d_out, h_out, event, st
     return ascii_.value != 0
 
 
+def _replay_plan(graph_slots, stream_slots, device, keys, first_slot=0):
+    """ctypes arrays for ``t2p_serving_replay_many``: step i = graph ``keys[i]`` of slot ``(first_slot + i) % depth`` on that
+    slot's stream (built once, replayed many times)."""
+    n, depth = len(keys), len(graph_slots)
+    execs, streams = (_lib.C.c_void_p * n)(), (_lib.C.c_void_p * n)()
+    for i, key in enumerate(keys):
+        sl = (first_slot + i) % depth
+        execs[i] = graph_slots[sl].graphs[key].raw_cuda_graph_exec()
+        st = stream_slots[sl].stream
+        streams[i] = st.cuda_stream if st is not None else _lib.stream_ptr(device)
+    return execs, streams, n
+
+
 class _Slot:
     """One in-flight batch: staging buffers both ways, the text embedding, workspaces, a stream and its graphs."""
 
@@ -257,6 +270,16 @@ class OnlineRetrievalEngine:
 
     def replay(self, key=0, slot: int = 0):
         self.slots[slot].graphs[key].replay()
+
+    def replay_plan(self, keys: Sequence, first_slot: int = 0):
+        """Plan for ``replay_many``: step i replays the captured graph ``keys[i]`` on slot ``(first_slot + i) % depth``."""
+        return _replay_plan(self.slots, self.slots, self.device, keys, first_slot)
+
+    def replay_many(self, plan, fork_join: bool = True):
+        """Launch every step of the plan back to back from native code (device-resident inputs; no interpreter between the
+        launches).  ``fork_join``: the slots' streams first wait for the current stream and the current stream waits for
+        them at the end (events recorded around the call bracket the region); otherwise synchronise the slots yourself."""
+        _lib.check(self.lib.t2p_serving_replay_many(*plan, _lib.stream_ptr(self.device), int(fork_join)), "serving_replay_many")
 
     # ---- end-to-end user calls ------------------------------------------------------------------------------------
     def _stage(self, descriptions: Sequence[str], slot: int) -> bool:
@@ -544,6 +567,14 @@ class ShardedOnlineRetrievalEngine:
 
     def replay(self, key=0, slot: int = 0):
         self.slots[slot].graphs[key].replay()
+
+    def replay_plan(self, keys: Sequence, first_slot: int = 0):
+        return _replay_plan(self.slots, self.eng.slots, self.eng.device, keys, first_slot)
+
+    def replay_many(self, plan, fork_join: bool = True):
+        """Collective in p2p mode: every rank must launch the same sequence of (slot, step)."""
+        e = self.eng
+        _lib.check(e.lib.t2p_serving_replay_many(*plan, _lib.stream_ptr(e.device), int(fork_join)), "serving_replay_many")
 
     def _enqueue_query(self, slot: int, descriptions, graph_key=None):
         e, s = self.eng, self.slots[slot]

@@ -210,11 +210,14 @@ retrieve_merge_kernel(const float* __restrict__ q, const float* __restrict__ db,
   }
 }
 
-// merge of R per-shard lists (float64 scores, int64 global indices): one warp per query
-__global__ void __launch_bounds__(32)
+// merge of R per-shard lists (float64 scores, int64 global indices): one warp per query, 8 queries per CTA (few fat CTAs: small
+// CTAs scattered over every SM get in the way of the cluster launches of the text encoder of the next batch)
+constexpr int MERGE_WARPS = 8;
+__global__ void __launch_bounds__(32 * MERGE_WARPS)
 topk_merge_kernel(const double* __restrict__ scores, const int64_t* __restrict__ idx, int R, int B, int k_in, int k_out,
                   double* __restrict__ out_s, int64_t* __restrict__ out_i) {
-  const int qi = blockIdx.x, lane = threadIdx.x;
+  const int qi = blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (qi >= B) return;
   const double NINF = __longlong_as_double(0xfff0000000000000LL);
   const int64_t IMAX = 0x7fffffffffffffffLL;
   WarpTopK<double, int64_t> top;
@@ -347,7 +350,8 @@ int t2p_topk_merge(const double* d_scores, const int64_t* d_idx, int R, int B, i
                    int64_t* d_out_idx, t2p_stream stream) {
   T2P_REQUIRE(d_scores && d_idx && d_out_scores && d_out_idx, T2P_ERR_INVALID, "topk_merge: null argument");
   T2P_REQUIRE(R >= 1 && B >= 1 && k_in >= 1 && k_out >= 1 && k_out <= 32, T2P_ERR_INVALID, "topk_merge: bad sizes");
-  topk_merge_kernel<<<B, 32, 0, as_stream(stream)>>>(d_scores, d_idx, R, B, k_in, k_out, d_out_scores, d_out_idx);
+  topk_merge_kernel<<<(B + MERGE_WARPS - 1) / MERGE_WARPS, 32 * MERGE_WARPS, 0, as_stream(stream)>>>(d_scores, d_idx, R, B, k_in, k_out,
+                                                                                                   d_out_scores, d_out_idx);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

@@ -119,6 +119,35 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  int spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    if (++spins > 400) __trap();
+  }
+}
+__device__ __forceinline__ bool scan_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void scan_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -249,41 +278,81 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    // One thread feeds the tensor pipe, and it shares its scheduler with an epilogue warp: every instruction between two
+    // tcgen05.mma is on the critical path (the first version rebuilt descriptors and re-tested the mode per K chunk: ~900
+    // cycles per chunk against 256 of MMA time).  The common mode (query tile in tensor memory) gets its own lean loop.
+    // The whole warp runs the (warp-uniform) control flow and one ELECTED lane issues the tcgen05 instructions: inside a
+    // per-thread branch (`if (lane == 0)`) the compiler wraps every UTCHMMA in an elect / branch loop.
+    if (p.a_tmem && !(p.debug & 1)) {
+      const uint32_t idesc = umma_idesc_tf32(TC_QM, tile_n);
+      const uint64_t desc0 = umma_desc_sw128_kmajor(smem_u32(st_smem));
+      const uint32_t pitch16 = (uint32_t)p.st_pitch >> 4;  // the address field of the descriptor counts 16-byte units
+      const uint32_t a0 = tmem_base + TC_Q_COL;
+      const uint32_t full0 = smem_u32(&sm->full[0]), empty0 = smem_u32(&sm->empty[0]);
+      const int stages = p.stages;
+      mbar_wait(&sm->q_full, 0);
+      if (lane == 0) STR(3);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&sm->tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem_base + acc * TC_TILE_MAX;
+        for (int kc = 0; kc < nch; ++kc) {
+          mbar_wait_addr(full0 + 8 * stage, ph);
+          tc_fence_after_sync();
+          if (scan_elect_one()) {
+            const uint64_t b_desc = desc0 + (uint64_t)(stage * pitch16);
+            const uint32_t a_col = a0 + kc * 32;
+            umma_tf32_ts(d_tmem, a_col, b_desc, idesc, kc != 0);
+            umma_tf32_ts(d_tmem, a_col + 8, b_desc + 2, idesc, true);
+            umma_tf32_ts(d_tmem, a_col + 16, b_desc + 4, idesc, true);
+            umma_tf32_ts(d_tmem, a_col + 24, b_desc + 6, idesc, true);
+            umma_commit_addr(empty0 + 8 * stage);
+            if (kc == nch - 1) umma_commit(&sm->tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; ph ^= 1; }
+        }
+        if (lane == 0) STR(8 + lt);
+      }
+    } else if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(TC_QM, tile_n);
       const uint32_t q_addr = smem_u32(q_smem), st_addr = smem_u32(st_smem);
       WAIT(&sm->q_full, 0);
       STR(3);
       int stage = 0;
       uint32_t ph = 0;
-      for (int lt = 0; lt < my_tiles; ++lt) {
-        const int acc = lt & 1;
-        WAIT(&sm->tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * TC_TILE_MAX;
-        for (int kc = 0; kc < nch; ++kc) {
-          WAIT(&sm->full[stage], ph);
+      {
+        for (int lt = 0; lt < my_tiles; ++lt) {
+          const int acc = lt & 1;
+          WAIT(&sm->tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
           tc_fence_after_sync();
-          // A = queries (M = 128 TMEM lanes), B = DB rows (N = tile_n columns); which of them is resident depends on the mode
-          const uint64_t res_desc = umma_desc_sw128_kmajor(q_addr + kc * p.q_pitch);
-          const uint64_t str_desc = umma_desc_sw128_kmajor(st_addr + stage * p.st_pitch);
-          const uint64_t a_desc = p.qstream ? str_desc : res_desc;
-          const uint64_t b_desc = p.qstream ? res_desc : str_desc;
-          if (p.debug & 1) {
-          } else if (p.a_tmem) {
+          const uint32_t d_tmem = tmem_base + acc * TC_TILE_MAX;
+          for (int kc = 0; kc < nch; ++kc) {
+            WAIT(&sm->full[stage], ph);
+            tc_fence_after_sync();
+            // A = queries (M = 128 TMEM lanes), B = DB rows (N = tile_n columns); which of them is resident depends on the mode
+            const uint64_t res_desc = umma_desc_sw128_kmajor(q_addr + kc * p.q_pitch);
+            const uint64_t str_desc = umma_desc_sw128_kmajor(st_addr + stage * p.st_pitch);
+            const uint64_t a_desc = p.qstream ? str_desc : res_desc;
+            const uint64_t b_desc = p.qstream ? res_desc : str_desc;
+            if (p.debug & 1) {
+            } else if (p.a_tmem) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)  // A: 8 tensor-memory columns per instruction
-              umma_tf32_ts(d_tmem, tmem_base + TC_Q_COL + kc * 32 + ks * 8, str_desc + 2 * ks, idesc, (kc | ks) != 0);
-          } else {
+              for (int ks = 0; ks < 4; ++ks)  // A: 8 tensor-memory columns per instruction
+                umma_tf32_ts(d_tmem, tmem_base + TC_Q_COL + kc * 32 + ks * 8, str_desc + 2 * ks, idesc, (kc | ks) != 0);
+            } else {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
-              umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+              for (int ks = 0; ks < 4; ++ks)  // K = 8 tf32 = 32 bytes per instruction: +2 in the 16-byte address field
+                umma_tf32_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+            }
+            umma_commit(&sm->empty[stage]);
+            if (++stage == p.stages) { stage = 0; ph ^= 1; }
           }
-          umma_commit(&sm->empty[stage]);
-          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          umma_commit(&sm->tmem_full[acc]);
+          STR(8 + lt);
         }
-        umma_commit(&sm->tmem_full[acc]);
-        STR(8 + lt);
       }
     }
     __syncwarp();
@@ -301,20 +370,49 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int subs = p.epi_warps >> 2;
     const uint32_t low_mask = (1u << p.nb_bits) - 1u;
     if (p.a_tmem) {
-      // the query tile goes to tensor memory once: TMEM lane = query row (rows 64.. mirror 0..63 in dup mode), column = channel
-      // the warps of a quadrant take alternate 32-channel blocks
-      const int qr = q0 + (p.dup ? (tl & 63) : tl);
-      const float4* src = reinterpret_cast<const float4*>(q_rows + (size_t)min(qr, p.B - 1) * p.D);
-        for (int c0 = 32 * sub; c0 < p.D; c0 += 32 * subs) {
-          uint32_t v[32];
+      // The query tile goes to tensor memory once: TMEM lane = query row (rows 64.. mirror 0..63 in dup mode), column = channel.
+      // A warp owns the 32 rows of its lane quadrant and moves them in blocks of 32 channels: coalesced 16-byte loads (8 lanes
+      // per row), a transpose through the warp's 4 KB of shared memory (16-byte units XOR-swizzled by the row: conflict-free
+      // both ways), then lane = row reads its 32 channels back for one tcgen05.st.  (A lane reading its own row straight from
+      // global memory costs 32 L1 wavefronts per load instruction: 5 us per CTA.)  The warps of a quadrant take alternate blocks.
+      const uint32_t xbuf = smem_u32(cand_smem + (warp - 2) * (TC_CAND_CAP * 32));
+      const int row_base = q0 + (p.dup ? (quad & 1) * 32 : quad * 32);
+      const int unit = lane & 7, rsub = lane >> 3;
+      auto load_block = [&](float4 (&x)[8], int c0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 x = qr < p.B ? __ldg(src + (c0 >> 2) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * i] = __float_as_uint(x.x); v[4 * i + 1] = __float_as_uint(x.y);
-            v[4 * i + 2] = __float_as_uint(x.z); v[4 * i + 3] = __float_as_uint(x.w);
-          }
-          scan_tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + TC_Q_COL + c0, v);
+        for (int i = 0; i < 8; ++i) {
+          const int qr = row_base + 4 * i + rsub;
+          x[i] = qr < p.B ? __ldg(reinterpret_cast<const float4*>(q_rows + (size_t)qr * p.D + c0) + unit) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      const int step = 32 * subs;
+      float4 x[8];
+      int c0 = 32 * sub;
+      if (c0 < p.D) load_block(x, c0);
+      for (; c0 < p.D; c0 += step) {
+        float4 nx[8];
+        const bool more = c0 + step < p.D;
+        if (more) load_block(nx, c0 + step);  // in flight while this block is transposed
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + rsub;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xbuf + r * 128 + ((unit ^ (r & 7)) << 4)), "f"(x[i].x),
+                       "f"(x[i].y), "f"(x[i].z), "f"(x[i].w));
+        }
+        __syncwarp();
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                       : "r"(xbuf + lane * 128 + ((j ^ (lane & 7)) << 4)));
+        scan_tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + TC_Q_COL + c0, v);
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = nx[i];
+        }
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before_sync();
       __syncwarp();
@@ -469,18 +567,15 @@ struct SelParams {
   int64_t idx_base;
 };
 
-__global__ void __launch_bounds__(SEL_THREADS, 3)
-retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, const SelParams p,
-                       const uint32_t* __restrict__ part_keys, const float* __restrict__ db_norm2_max,
-                       double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats,
-                       const int32_t* __restrict__ only_flagged) {
-  extern __shared__ __align__(16) uint8_t sel_raw[];
-  // second stage behind retrieve_select_warp_kernel: only the queries it could not certify are (re)done here
-  if (only_flagged != nullptr && only_flagged[blockIdx.x] == 0) return;
+// one query by the whole CTA (every thread of the CTA calls it with the same qi)
+__device__ void select_one_query(const int qi, uint8_t* sel_raw, const float* __restrict__ q, const float* __restrict__ db,
+                                 const SelParams& p, const uint32_t* __restrict__ part_keys,
+                                 const float* __restrict__ db_norm2_max, double* __restrict__ out_s, int64_t* __restrict__ out_i,
+                                 int32_t* __restrict__ stats) {
   SelSmem* sm = reinterpret_cast<SelSmem*>(sel_raw);
   float* qs = reinterpret_cast<float*>(sel_raw + sizeof(SelSmem));  // [D]
   uint32_t* keys = reinterpret_cast<uint32_t*>(qs + p.D);             // [nsrc*KP]
-  const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.D, N = p.N, KP = p.KP, NC = p.NC, k = p.k, nsrc = p.nsrc;
   const int total = nsrc * KP;
   const uint32_t low_mask = (1u << p.nb_bits) - 1u;
@@ -794,6 +889,22 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
   }
 }
 
+// grid = B CTAs, one query each (only_flagged == nullptr), or -- second stage behind retrieve_select_warp_kernel -- a small grid
+// whose CTAs walk over the queries and redo only the ones the warp kernel could not certify (usually none: the launch then costs
+// a handful of CTAs reading their flags instead of B CTAs spread over every SM)
+__global__ void __launch_bounds__(SEL_THREADS, 3)
+retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db, const SelParams p,
+                       const uint32_t* __restrict__ part_keys, const float* __restrict__ db_norm2_max,
+                       double* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ stats,
+                       const int32_t* __restrict__ only_flagged) {
+  extern __shared__ __align__(16) uint8_t sel_raw[];
+  for (int qi = blockIdx.x; qi < p.B; qi += gridDim.x) {
+    if (only_flagged != nullptr && only_flagged[qi] == 0) continue;  // CTA-uniform
+    select_one_query(qi, sel_raw, q, db, p, part_keys, db_norm2_max, out_s, out_i, stats);
+    __syncthreads();  // shared memory is reused by the next query
+  }
+}
+
 // ---- select, one WARP per query ------------------------------------------------------------------------------------------
 // The per-query work of the select is tiny (a few hundred keys, <= 32 rows to re-score); a 256-thread CTA per query spends
 // its time in barriers and occupies an SM slot for ~17 us.  Here a warp does a whole query: the sorted key lists of the scan
@@ -802,7 +913,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
 // flight), ranked with shuffles and CERTIFIED against the best remaining key exactly like retrieve_select_kernel; if that
 // fails the next 16 are added; a query that still cannot be certified is flagged for the CTA-per-query kernel (which also
 // owns the exact rescan).  8 queries per CTA: 64 queries occupy 8 SM slots for a few microseconds instead of 64 for 17.
-constexpr int SELW_WARPS = 8;
+constexpr int SELW_WARPS = 16;  // queries per CTA: few fat CTAs (see topk_merge_kernel)
 constexpr int SELW_MAX_LPL = 10;  // lists per lane: nsrc <= 320
 
 __global__ void __launch_bounds__(32 * SELW_WARPS)
@@ -1058,6 +1169,8 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
   if (fixed + 2 * (size_t)p.st_pitch > budget) return p;
   p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / p.st_pitch);
   p.stages = std::min(p.stages, std::max(2, nch * (p.qstream ? p.qtiles : p.tiles_per_cta)));
+  static const int stage_cap = [] { const char* e = getenv("T2P_SCAN_STAGES"); return e ? atoi(e) : 0; }();
+  if (stage_cap >= 2) p.stages = std::min(p.stages, stage_cap);
   p.scan_smem = fixed + (size_t)p.stages * p.st_pitch;
   p.sel_smem = sizeof(SelSmem) + (size_t)D * 4 + (size_t)p.nsrc * p.KP * 4;
   if (p.sel_smem > 200 * 1024) return p;
@@ -1106,6 +1219,8 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
   T2P_TRY(make_tmap_rows(&tq, d_q, B, D, sp.q_box_rows));
   T2P_TRY(make_tmap_rows(&tdb, d_db, N, D, sp.db_box_rows));
   dim3 grid(p.G, p.qstream ? 1 : p.qtiles);
+  // (launching the scan as 8-CTA clusters, so that it takes and returns SMs in the GPC-aligned groups the text encoder's
+  // clusters need, was measured: 5-8 % slower per step than plain CTAs)
   if (p.KP == 16) {
     T2P_CUDA(cudaFuncSetAttribute(retrieve_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.scan_smem));
     retrieve_scan_tc_kernel<16><<<grid, 32 * (2 + scan_epi_warps()), p.scan_smem, s>>>(tq, tdb, sp, d_q, part);
@@ -1130,8 +1245,8 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
         d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats, flagged);
     T2P_LAUNCH_CHECK();
   }
-  retrieve_select_kernel<<<B, SEL_THREADS, p.sel_smem, s>>>(d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats,
-                                                            warp_path ? flagged : nullptr);
+  retrieve_select_kernel<<<warp_path ? std::min(B, 64) : B, SEL_THREADS, p.sel_smem, s>>>(
+      d_q, d_db, q, part, d_db_norm2_max, d_out_scores, d_out_idx, d_stats, warp_path ? flagged : nullptr);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }

@@ -23,3 +23,7 @@ print(f"setup done {rel(1):.2f}  Q in TMEM {rel(2):.2f}  MMA thread past q_full 
 for lt in range(32):
     if buf[8 + lt]:
         print(f"tile {lt:2d}: MMAs issued {rel(8+lt):7.2f}  accumulator ready {rel(40+lt):7.2f}  scanned {rel(72+lt):7.2f}")
+if buf[96]:
+    print("tile 2, per K chunk: [before wait, after wait, after 4 MMAs + commit] us")
+    for kc in range(8):
+        print(f"  kc {kc}: {rel(96+3*kc):7.2f} {rel(97+3*kc):7.2f} {rel(98+3*kc):7.2f}")

@@ -38,7 +38,7 @@ N_DB_COPIES = 32  # rotate DB copies (32 x 10 MB > 126 MB L2) so that every step
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/r02_online_full.txt,
 # same command line, N = 1): the scan streams the DB once (10.34 MB vs 10.32 MB algorithmic) + the selects' candidate rows
 # (0.77 + 0.06 MB); the LSTM reads its weights + table
-NCU_TRAFFIC = {"topk": 10335744 + 773888 + 57856, "lstm": 2510848}
+NCU_TRAFFIC = {"topk": 10370560 + 774144 + 67072, "lstm": 2509568}
 TRAFFIC_SOURCE = ("constant from the committed `ncu --set full` capture of this command line (profiles/r02_online_full.txt), per launch; "
                   "NOT observed by this run (a run under ncu is never a bench value)")
 

@@ -913,7 +913,8 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
 // flight), ranked with shuffles and CERTIFIED against the best remaining key exactly like retrieve_select_kernel; if that
 // fails the next 16 are added; a query that still cannot be certified is flagged for the CTA-per-query kernel (which also
 // owns the exact rescan).  8 queries per CTA: 64 queries occupy 8 SM slots for a few microseconds instead of 64 for 17.
-constexpr int SELW_WARPS = 16;  // queries per CTA: few fat CTAs (see topk_merge_kernel)
+constexpr int SELW_WARPS = 2;   // queries per CTA: the kernel is instruction-bound per warp (~6k instructions per query), so the
+                                // warps are spread over many SMs (16 per CTA: 26 us for 64 queries on 4 SMs)
 constexpr int SELW_MAX_LPL = 10;  // lists per lane: nsrc <= 320
 
 __global__ void __launch_bounds__(32 * SELW_WARPS)
@@ -963,6 +964,7 @@ retrieve_select_warp_kernel(const float* __restrict__ q, const float* __restrict
     bpos = 0;
 #pragma unroll
     for (int i = 0; i < SELW_MAX_LPL; ++i) {
+      if (32 * i >= nsrc) break;  // warp-uniform: no lane owns a list beyond this
       const int l = lane + 32 * i;
       const int c = (int)((cur >> (6 * i)) & 63ull);
       if (l < nsrc && c < KP) {

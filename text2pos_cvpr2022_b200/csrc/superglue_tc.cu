@@ -143,21 +143,38 @@ struct SgtIssue {  // state of the MMA issuer (compute thread 0)
   uint32_t phase;
 };
 
-// one weight stage against A chunk `a_chunk`: 4 K steps x 3 products of M = 128, N = 128, K = 16
+__device__ __forceinline__ bool sgt_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// one weight stage against A chunk `a_chunk`: 4 K steps x 3 products of M = 128, N = 128, K = 16.  Called by ALL lanes of warp
+// 0 (warp-uniform control flow); one elected lane issues the tcgen05 instructions -- inside a per-thread branch (`if (tid ==
+// 0)`) the compiler wraps every UTCHMMA in an elect / branch loop and the issuing thread, not the tensor pipe, paces the
+// products.  `done`: also commit to mma_done (by the lane that issued the MMAs it tracks).
 __device__ __forceinline__ void sgt_mma_stage(SgtBars* bars, uint32_t a_addr, uint32_t w_addr, SgtIssue& is, uint32_t tmem_dst,
-                                              int a_chunk, bool accumulate) {
+                                              int a_chunk, bool accumulate, bool done) {
   mbar_wait(&bars->full[is.stage], is.phase);
   tc_fence_after_sync();
-  const uint32_t idesc = sgt_idesc(SGT_ROWS, 128);
-  const uint32_t wa = w_addr + is.stage * SGT_W_STAGE;
+  if (sgt_elect_one()) {
+    const uint32_t idesc = sgt_idesc(SGT_ROWS, 128);
+    const uint32_t wa = w_addr + is.stage * SGT_W_STAGE;
 #pragma unroll
-  for (int prod = 0; prod < 3; ++prod) {  // A_hi.W_hi, A_hi.W_lo, A_lo.W_hi
-    const uint64_t a_desc = umma_desc_sw128_kmajor(a_addr + (prod == 2 ? SGT_A_PART : 0) + a_chunk * SGT_A_CHUNK);
-    const uint64_t b_desc = umma_desc_sw128_kmajor(wa + (prod == 1 ? SGT_W_PART : 0));
+    for (int prod = 0; prod < 3; ++prod) {  // A_hi.W_hi, A_hi.W_lo, A_lo.W_hi
+      const uint64_t a_desc = umma_desc_sw128_kmajor(a_addr + (prod == 2 ? SGT_A_PART : 0) + a_chunk * SGT_A_CHUNK);
+      const uint64_t b_desc = umma_desc_sw128_kmajor(wa + (prod == 1 ? SGT_W_PART : 0));
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) sgt_umma(tmem_dst, a_desc + 2 * ks, b_desc + 2 * ks, idesc, accumulate || prod != 0 || ks != 0);
+      for (int ks = 0; ks < 4; ++ks) sgt_umma(tmem_dst, a_desc + 2 * ks, b_desc + 2 * ks, idesc, accumulate || prod != 0 || ks != 0);
+    }
+    umma_commit(&bars->empty[is.stage]);
+    if (done) umma_commit(&bars->mma_done);
   }
-  umma_commit(&bars->empty[is.stage]);
+  __syncwarp();
   if (++is.stage == SGT_W_STAGES) { is.stage = 0; is.phase ^= 1; }
 }
 
@@ -270,12 +287,12 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
       // ---- q, k, v = X . Wq', Wk', Wv' (head-major columns) ----
       sgt_tmem_to_A<false>(trow, SGT_X, half, row, 1.f, nullptr, A, amax);
       publish_A();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after_sync();
 #pragma unroll 1
         for (int mat = 0; mat < 3; ++mat)
-          for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1 + mat * 128, kc, kc != 0);
-        umma_commit(&bars->mma_done);
+          for (int kc = 0; kc < 2; ++kc)
+            sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1 + mat * 128, kc, kc != 0, mat == 2 && kc == 1);
       }
       wait_done();
       // ---- attention: K rows -> shared memory, scores + softmax in registers, then V rows, message -> A operand ----
@@ -384,46 +401,43 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
       }
       publish_A();
       // ---- merged = message . Wmerge' -> R1 ----
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after_sync();
-        for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0);
-        umma_commit(&bars->mma_done);
+        for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0, kc == 1);
       }
       wait_done();
       // ---- hidden = relu([X | merged] . W0 + b0): K = 256 in two A operands, N = 256 in two 128-column blocks (R2, R3) ----
       sgt_tmem_to_A<false>(trow, SGT_X, half, row, 1.f, nullptr, A, amax);
       publish_A();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after_sync();
         for (int nb = 0; nb < 2; ++nb)
-          for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R2 + nb * 128, kc, kc != 0);
-        umma_commit(&bars->mma_done);
+          for (int kc = 0; kc < 2; ++kc)
+            sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R2 + nb * 128, kc, kc != 0, nb == 1 && kc == 1);
       }
       wait_done();
       sgt_tmem_to_A<false>(trow, SGT_R1, half, row, SGT_UNSCALE, bm, A, amax);  // merged + bias
       publish_A();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after_sync();
         for (int nb = 0; nb < 2; ++nb)
-          for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R2 + nb * 128, kc, true);
-        umma_commit(&bars->mma_done);
+          for (int kc = 0; kc < 2; ++kc)
+            sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R2 + nb * 128, kc, true, nb == 1 && kc == 1);
       }
       wait_done();
       // ---- delta = hidden . W3 -> R1 ----
       sgt_tmem_to_A<true>(trow, SGT_R2, half, row, SGT_UNSCALE, b0, A, amax);
       publish_A();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after_sync();
-        for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0);
-        umma_commit(&bars->mma_done);
+        for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0, kc == 1);
       }
       wait_done();
       sgt_tmem_to_A<true>(trow, SGT_R3, half, row, SGT_UNSCALE, b0 + 128, A, amax);
       publish_A();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after_sync();
-        for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, true);
-        umma_commit(&bars->mma_done);
+        for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, true, kc == 1);
       }
       wait_done();
       // ---- X += delta + b3 ----
@@ -446,10 +460,9 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
     // ---- final projection -> mdesc rows in shared memory ----
     sgt_tmem_to_A<false>(trow, SGT_X, half, row, 1.f, nullptr, A, amax);
     publish_A();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after_sync();
-      for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0);
-      umma_commit(&bars->mma_done);
+      for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0, kc == 1);
     }
     wait_done();
     {

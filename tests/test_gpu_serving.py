@@ -83,6 +83,39 @@ def test_engine_pipelined_submit_collect_equals_query(coarse_model):
     np.testing.assert_array_equal(i0, want[0][0])
 
 
+def test_replay_many_runs_every_captured_step_on_its_slot(coarse_model):
+    """Device-resident loop (``t2p_serving_replay_many``): K captured steps launched by one native call, forked from and joined
+    into the current stream -- every slot ends up with the result of the text staged in it, for both captured DBs."""
+    B, N, k, depth = 8, 2000, 10, 3
+    db_a = syn.synth_db_embeddings(24, N, 256).cuda()
+    db_b = syn.synth_db_embeddings(25, N, 256).cuda()
+    db_b = db_b * (db_a.norm(dim=1).max() / db_b.norm(dim=1).max())  # alternative copies share the norm bound of the engine's DB
+    ref = OnlineRetrievalEngine(coarse_model, db_a, k=k, max_batch=B, max_tokens=64)
+    eng = OnlineRetrievalEngine(coarse_model, db_a, k=k, max_batch=B, max_tokens=64, depth=depth)
+    batches = [syn.synth_queries(40 + i, B) for i in range(depth)]
+    for sl, b in enumerate(batches):  # stage the text of slot sl once (resident from now on)
+        used, ascii_ = eng.vocab.stage_texts(b, eng.slots[sl].h_stage)
+        assert ascii_
+        eng.slots[sl].d_stage.copy_(eng.slots[sl].h_stage)
+    eng.capture_all("a", db_a)
+    eng.capture_all("b", db_b)
+    for key, db in (("a", db_a), ("b", db_b)):
+        for sl in range(depth):
+            eng.slots[sl].out_idx.fill_(-7)
+        plan = eng.replay_plan([key] * (2 * depth))  # every slot twice
+        ev = torch.cuda.Event()
+        eng.replay_many(plan)
+        ev.record()          # recorded on the current stream AFTER the join: covers all slots
+        ev.synchronize()
+        ref.set_db(db)
+        for sl, b in enumerate(batches):
+            want_i, want_s = ref.query(b)
+            np.testing.assert_array_equal(eng.slots[sl].out_idx.cpu().numpy(), want_i)
+            np.testing.assert_array_equal(eng.slots[sl].out_scores.cpu().numpy(), want_s)
+    with pytest.raises(KeyError):
+        eng.replay_plan(["missing"])
+
+
 def test_device_tokenizer_matches_the_python_rules():
     """t2p_tokenize_device == models/modules.py:60-72 (remove '.' ',', lower, split on whitespace, OOV -> 0, zero pad) on
     templated hints and on edge cases: punctuation inside words, runs of separators, empty and over-long descriptions."""

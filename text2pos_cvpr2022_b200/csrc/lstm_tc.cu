@@ -140,6 +140,20 @@ __device__ __forceinline__ float ltc_ex2(float x) {
 __device__ __forceinline__ float ltc_sigmoid(float x) { return ltc_rcp(1.f + ltc_ex2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float ltc_tanh(float x) { return fmaf(-2.f, ltc_rcp(1.f + ltc_ex2(2.885390081777927f * x)), 1.f); }
 
+#ifdef T2P_LSTM_TRACE  // tools/make_lstm_trace.py: %globaltimer stamps of cluster 0 / CTA rank 0, steps 20..23, per group and event
+__device__ unsigned long long lstm_trace[4 * LTC_MAXG * 8];
+#define LTR(step, g, ev)                                                                     \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && (step) >= 20 && (step) < 24) {                                    \
+      unsigned long long t_;                                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+      lstm_trace[(((step) - 20) * LTC_MAXG + (g)) * 8 + (ev)] = t_;                          \
+    }                                                                                        \
+  } while (0)
+#else
+#define LTR(step, g, ev) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates (i,f,g,o) of (token, unit)
                const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (LTC_W_HALFS per slice)
@@ -242,7 +256,12 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   if (warp == LTC_EPI_WARPS) {
     // ===== control warp (warp-uniform loop; one elected lane issues): per step and group wait(h) -> MMAs -> commit.  One
     // barrier per buffer: splitting it per source CTA to start the MMAs of early slices sooner was measured SLOWER (8
-    // waits + 8 proxy fences per step cost more than the 48 MMAs they would hide). =====
+    // waits + 8 proxy fences per step cost more than the 48 MMAs they would hide).  Also measured (%globaltimer trace,
+    // tools/diag_lstm_trace.py): a step of a group is one dependent chain of ~1.75 us -- MMA issue 0.3, completion + wake-up
+    // 0.2, cell update 0.45, staging barrier + copy issue 0.1, SM-to-SM copies until the slowest of the 8 CTAs has delivered
+    // 0.6-0.7 -- and the four groups run that chain side by side.  Two control warps (groups {0,2} / {1,3}), polling instead of
+    // parked waits, and a dedicated copy warp behind an mbarrier instead of the named barrier all left the chain, hence the
+    // step, where it was. =====
     const uint32_t idesc = umma_idesc_f16(128, LTC_NS);
     const uint32_t hb_addr = smem_u32(hb_smem);
     for (int step = 0; step < steps; ++step) {
@@ -255,6 +274,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
           if (lane == 0) mbar_expect_tx(&bars->h_bar[g][cur], step_bytes[g]);  // re-arm for step + 2
           // no proxy fence: h arrives through the async proxy (bulk copies) and the UMMA reads through it too
         }
+        if (lane == 0) LTR(step, g, 0);
         tc_fence_after_sync();
         if (ltc_elect_one()) {
           const uint32_t hb = hb_addr + (g * 2 + cur) * LTC_HB_BUF;
@@ -271,6 +291,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
             }
           }
           umma_commit(&bars->mma_bar[g]);
+          LTR(step, g, 1);
         }
         __syncwarp();
       }
@@ -341,10 +362,12 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
           for (int e = 0; e < 2; ++e) xn[gi][e] = __ldg(xp_base + (size_t)token_at(gi, e, step + 1) * LTC_H);
         }
         mbar_wait(&bars->mma_bar[g], (uint32_t)(step & 1));
+        if ((warp & 7) == 0 && lane == 0) LTR(step, g, 2);
         tc_fence_after_sync();
         uint32_t v[8];
         tmem_ld_32x8(tmem_src + g * LTC_NS, v);
         tmem_ld_wait();
+        if ((warp & 7) == 0 && lane == 0) LTR(step, g, 3);
         tc_fence_before_sync();
         // 4x4 block transpose (blocks of 2 sequences) over the 4 lanes of a unit as two butterfly stages (xor 2, xor 1);
         // every register index is static and every choice a predicated select, so the warp never diverges.  Lane g4 ends
@@ -396,10 +419,13 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
             }
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the bulk copy (async proxy)
           }
+          if ((warp & 7) == 0 && lane == 0) LTR(step, g, 4);
           asm volatile("bar.sync %0, 256;" ::"r"(1 + gs) : "memory");  // the 8 warps of this set: the slice is complete
+          if ((warp & 7) == 0 && lane == 0) LTR(step, g, 5);
           if (ltc_elect_one())
             ltc_bulk_copy(rdst + (uint32_t)(g * 2 + nxt) * LTC_HB_BUF, smem_u32(slice), halves * 1024u,
                           rbar + (uint32_t)(g * 2 + nxt) * 8u);
+          if ((warp & 7) == 0 && lane == 0) LTR(step, g, 6);
         }
       }
     }
@@ -417,6 +443,14 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
   tc_fence_after_sync();
   if (warp == LTC_EPI_WARPS) tmem_dealloc<LTC_TMEM_COLS>(tmem_base);
 }
+
+#ifdef T2P_LSTM_TRACE
+}  // namespace t2p
+extern "C" int t2p_debug_lstm_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, t2p::lstm_trace, sizeof(t2p::lstm_trace));
+}
+namespace t2p {
+#endif
 
 size_t lstm_tc_smem_bytes(int T) {
   return (size_t)LTC_MAXG * 2 * LTC_HB_BUF + LTC_STAGE_BYTES + sizeof(LtcBars) + ((size_t)LTC_MAXG * LTC_NS * T + LTC_MAXG * LTC_NS) * sizeof(int) + 64;

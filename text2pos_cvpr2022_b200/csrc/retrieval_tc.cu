@@ -188,7 +188,8 @@ struct ScanParams {
                    // once by the epilogue warps -- all of shared memory is the DB ring (the 128 KB tile left room for 2 stages)
   int slack;       // bytes after the ring the UMMA may read past a short resident tile (SS forms only)
   int epi_warps;   // 4 or 8 epilogue warps (1 or 2 key lists per (query, CTA, half))
-  int debug;       // T2P_SCAN_DEBUG knock-outs (tools only; results are wrong): 1 = no UMMAs, 2 = no column scan
+  int debug;       // knock-outs of the trace build (T2P_SCAN_DEBUG; results are wrong): 1 = no UMMAs, 2 = no column scan;
+                   // always 0 in the product library
 };
 
 template <int KP>
@@ -232,10 +233,7 @@ retrieve_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const uint32_t tmem_base = sm->tmem_slot;
   if (threadIdx.x == 0) STR(1);
 
-  auto WAIT = [&](uint64_t* bar, uint32_t parity) {
-    if (p.debug & 4) mbar_wait(bar, parity);
-    else mbar_wait_spin(bar, parity);
-  };
+  auto WAIT = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };  // parked waits: polling measured slower
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -1171,8 +1169,6 @@ TcPlan tc_plan(int B, int N, int D, int k, int sms) {
   if (fixed + 2 * (size_t)p.st_pitch > budget) return p;
   p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / p.st_pitch);
   p.stages = std::min(p.stages, std::max(2, nch * (p.qstream ? p.qtiles : p.tiles_per_cta)));
-  static const int stage_cap = [] { const char* e = getenv("T2P_SCAN_STAGES"); return e ? atoi(e) : 0; }();
-  if (stage_cap >= 2) p.stages = std::min(p.stages, stage_cap);
   p.scan_smem = fixed + (size_t)p.stages * p.st_pitch;
   p.sel_smem = sizeof(SelSmem) + (size_t)D * 4 + (size_t)p.nsrc * p.KP * 4;
   if (p.sel_smem > 200 * 1024) return p;
@@ -1214,8 +1210,12 @@ int launch_retrieve_tc(const TcPlan& p, const float* d_q, const float* d_db, int
   sp.q_pitch = p.q_pitch; sp.st_pitch = p.st_pitch; sp.stages = p.stages;
   sp.nb_bits = p.nb_bits; sp.dup = p.dup; sp.qstream = p.qstream; sp.qtiles = p.qtiles;
   sp.a_tmem = p.a_tmem; sp.slack = p.slack;
+#ifdef T2P_SCAN_TRACE  // knock-out experiments (wrong results by design) exist only in the trace build, never in the product library
   static const int scan_debug = [] { const char* e = getenv("T2P_SCAN_DEBUG"); return e ? atoi(e) : 0; }();
   sp.debug = scan_debug;
+#else
+  sp.debug = 0;
+#endif
   sp.epi_warps = scan_epi_warps();
   CUtensorMap tq, tdb;
   T2P_TRY(make_tmap_rows(&tq, d_q, B, D, sp.q_box_rows));

@@ -58,15 +58,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Polling flavour (bounded as well) for single-thread roles on a latency-critical chain (an MMA issuer waiting for its operands):
-// nothing else wants the issue slots of that warp, and a parked thread wakes up later than a polling one notices.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  long long spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1ll << 28)) __trap();
-  }
-}
-
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

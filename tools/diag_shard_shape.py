@@ -12,8 +12,12 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from text2pos_cvpr2022_b200 import _lib  # noqa: E402
+
+if os.environ.get("T2P_DIAG_LIB"):  # an experimental build of the library (trace / knock-out experiments)
+    _lib.LIB_PATH = os.environ["T2P_DIAG_LIB"]
 import bench  # noqa: E402
-from text2pos_cvpr2022_b200 import _lib, synthetic as syn  # noqa: E402
+from text2pos_cvpr2022_b200 import synthetic as syn  # noqa: E402
 from text2pos_cvpr2022_b200.serving import OnlineRetrievalEngine  # noqa: E402
 
 

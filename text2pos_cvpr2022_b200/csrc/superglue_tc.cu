@@ -178,6 +178,20 @@ __device__ __forceinline__ void sgt_mma_stage(SgtBars* bars, uint32_t a_addr, ui
   if (++is.stage == SGT_W_STAGES) { is.stage = 0; is.phase ^= 1; }
 }
 
+#ifdef T2P_SGT_TRACE  // tools/make_sgt_trace.py: %globaltimer stamps of CTA 0 / thread 0 at the phase boundaries of layers 4 and 5
+__device__ unsigned long long sgt_trace[64];
+#define GTR(i)                                                          \
+  do {                                                                  \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) {              \
+      unsigned long long t_;                                            \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));            \
+      sgt_trace[(i)] = t_;                                              \
+    }                                                                   \
+  } while (0)
+#else
+#define GTR(i) do {} while (0)
+#endif
+
 template <int MS>  // MS >= max(M, N): compile-time bound of the attention source loop (16 or 32)
 __global__ void __launch_bounds__(SGT_THREADS, 1)
 superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_superglue_desc d,
@@ -281,12 +295,15 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
 
     const float inv_sqrt_dh = 1.f / sqrtf((float)SGT_DH);
     for (int layer = 0; layer < L; ++layer) {
+      const int tr0 = (layer == 4 || layer == 5) ? (layer - 4) * 16 : 64;
+      GTR(tr0 + 0);
       const float* bl = b_stream + (size_t)layer * SGT_BIAS_PER_LAYER;
       const float *bq = bl, *bk = bl + 128, *bv = bl + 256, *bm = bl + 384, *b0 = bl + 512, *b3 = bl + 768;
       const bool cross = d.is_cross[layer] != 0;
       // ---- q, k, v = X . Wq', Wk', Wv' (head-major columns) ----
       sgt_tmem_to_A<false>(trow, SGT_X, half, row, 1.f, nullptr, A, amax);
       publish_A();
+      GTR(tr0 + 1);
       if (warp == 0) {
         tc_fence_after_sync();
 #pragma unroll 1
@@ -295,6 +312,7 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
             sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1 + mat * 128, kc, kc != 0, mat == 2 && kc == 1);
       }
       wait_done();
+      GTR(tr0 + 2);
       // ---- attention: K rows -> shared memory, scores + softmax in registers, then V rows, message -> A operand ----
       const bool src_is0 = (side0 != cross);
       const int sn = src_is0 ? M : N;
@@ -321,27 +339,25 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
         float q[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) q[j] = fmaf(__uint_as_float(qv[j]), SGT_UNSCALE, __ldg(bq + h * SGT_DH + j));
+        // scores against the sn source rows of the sample: fully unrolled over the compile-time bound MS with the row index
+        // clamped (no branch, no select chain to place a score in its static register) and four partial sums per score (a
+        // single accumulator made every score a 32-deep dependent FMA chain: the attention was 43 % of a layer)
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < MS; ++j) p[hh][j] = 0.f;
-        if (row_valid) {
-#pragma unroll 1
-          for (int j = 0; j < sn; ++j) {  // dynamic loop (small code); the score lands in its static register by a select chain
-            const float4* kr = reinterpret_cast<const float4*>(KV + (s0 + j) * SGT_KV_PITCH + h * SGT_DH);
-            float acc = 0.f;
+        for (int j = 0; j < MS; ++j) {
+          const float4* kr = reinterpret_cast<const float4*>(KV + (s0 + min(j, sn - 1)) * SGT_KV_PITCH + h * SGT_DH);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 kk = kr[c];
-              acc = fmaf(q[4 * c], kk.x, acc);
-              acc = fmaf(q[4 * c + 1], kk.y, acc);
-              acc = fmaf(q[4 * c + 2], kk.z, acc);
-              acc = fmaf(q[4 * c + 3], kk.w, acc);
-            }
-            acc *= inv_sqrt_dh;
-            mx = fmaxf(mx, acc);
-#pragma unroll
-            for (int jj = 0; jj < MS; ++jj) p[hh][jj] = (jj == j) ? acc : p[hh][jj];
+          for (int c = 0; c < 8; ++c) {
+            const float4 kk = kr[c];
+            a0 = fmaf(q[4 * c], kk.x, a0);
+            a1 = fmaf(q[4 * c + 1], kk.y, a1);
+            a2 = fmaf(q[4 * c + 2], kk.z, a2);
+            a3 = fmaf(q[4 * c + 3], kk.w, a3);
           }
+          const float acc = ((a0 + a1) + (a2 + a3)) * inv_sqrt_dh;
+          p[hh][j] = acc;
+          mx = (j < sn) ? fmaxf(mx, acc) : mx;
         }
         float sum = 0.f;
 #pragma unroll
@@ -374,21 +390,17 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
         float a[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) a[c] = 0.f;
-        if (row_valid) {
-#pragma unroll 1
-          for (int j = 0; j < sn; ++j) {
-            float pj = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < MS; ++jj) pj = (jj == j) ? p[hh][jj] : pj;
-            const float4* vr = reinterpret_cast<const float4*>(KV + (s0 + j) * SGT_KV_PITCH + h * SGT_DH);
+        for (int j = 0; j < MS; ++j) {  // p[hh][j] = 0 beyond sn and for rows outside the tile's samples
+          const float pj = p[hh][j];
+          const float4* vr = reinterpret_cast<const float4*>(KV + (s0 + min(j, sn - 1)) * SGT_KV_PITCH + h * SGT_DH);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 vv = vr[c];
-              a[4 * c] = fmaf(pj, vv.x, a[4 * c]);
-              a[4 * c + 1] = fmaf(pj, vv.y, a[4 * c + 1]);
-              a[4 * c + 2] = fmaf(pj, vv.z, a[4 * c + 2]);
-              a[4 * c + 3] = fmaf(pj, vv.w, a[4 * c + 3]);
-            }
+          for (int c = 0; c < 8; ++c) {
+            const float4 vv = vr[c];
+            a[4 * c] = fmaf(pj, vv.x, a[4 * c]);
+            a[4 * c + 1] = fmaf(pj, vv.y, a[4 * c + 1]);
+            a[4 * c + 2] = fmaf(pj, vv.z, a[4 * c + 2]);
+            a[4 * c + 3] = fmaf(pj, vv.w, a[4 * c + 3]);
           }
         }
 #pragma unroll
@@ -400,15 +412,18 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
         }
       }
       publish_A();
+      GTR(tr0 + 3);
       // ---- merged = message . Wmerge' -> R1 ----
       if (warp == 0) {
         tc_fence_after_sync();
         for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0, kc == 1);
       }
       wait_done();
+      GTR(tr0 + 4);
       // ---- hidden = relu([X | merged] . W0 + b0): K = 256 in two A operands, N = 256 in two 128-column blocks (R2, R3) ----
       sgt_tmem_to_A<false>(trow, SGT_X, half, row, 1.f, nullptr, A, amax);
       publish_A();
+      GTR(tr0 + 5);
       if (warp == 0) {
         tc_fence_after_sync();
         for (int nb = 0; nb < 2; ++nb)
@@ -416,8 +431,10 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
             sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R2 + nb * 128, kc, kc != 0, nb == 1 && kc == 1);
       }
       wait_done();
+      GTR(tr0 + 6);
       sgt_tmem_to_A<false>(trow, SGT_R1, half, row, SGT_UNSCALE, bm, A, amax);  // merged + bias
       publish_A();
+      GTR(tr0 + 7);
       if (warp == 0) {
         tc_fence_after_sync();
         for (int nb = 0; nb < 2; ++nb)
@@ -425,21 +442,26 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
             sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R2 + nb * 128, kc, true, nb == 1 && kc == 1);
       }
       wait_done();
+      GTR(tr0 + 8);
       // ---- delta = hidden . W3 -> R1 ----
       sgt_tmem_to_A<true>(trow, SGT_R2, half, row, SGT_UNSCALE, b0, A, amax);
       publish_A();
+      GTR(tr0 + 9);
       if (warp == 0) {
         tc_fence_after_sync();
         for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, kc != 0, kc == 1);
       }
       wait_done();
+      GTR(tr0 + 10);
       sgt_tmem_to_A<true>(trow, SGT_R3, half, row, SGT_UNSCALE, b0 + 128, A, amax);
       publish_A();
+      GTR(tr0 + 11);
       if (warp == 0) {
         tc_fence_after_sync();
         for (int kc = 0; kc < 2; ++kc) sgt_mma_stage(bars, a_addr, w_addr, is, tmem_base + SGT_R1, kc, true, kc == 1);
       }
       wait_done();
+      GTR(tr0 + 12);
       // ---- X += delta + b3 ----
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -457,6 +479,7 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
       sgt_tmem_st_wait();
     }
 
+    GTR(40);
     // ---- final projection -> mdesc rows in shared memory ----
     sgt_tmem_to_A<false>(trow, SGT_X, half, row, 1.f, nullptr, A, amax);
     publish_A();
@@ -581,6 +604,7 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  GTR(41);
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
@@ -614,3 +638,9 @@ int launch_superglue_tc(const float* blob, const t2p_superglue_desc* desc, const
 }
 
 }  // namespace t2p
+
+#ifdef T2P_SGT_TRACE
+extern "C" int t2p_debug_sgt_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, t2p::sgt_trace, sizeof(t2p::sgt_trace));
+}
+#endif

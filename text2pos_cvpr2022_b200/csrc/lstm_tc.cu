@@ -47,7 +47,6 @@ constexpr int LTC_EPI_SETS = 2;    // epilogue warp sets: set s serves groups s,
 constexpr int LTC_EPI_WARPS = 8 * LTC_EPI_SETS;
 constexpr int LTC_GPS = LTC_MAXG / LTC_EPI_SETS;       // groups per epilogue set
 constexpr int LTC_THREADS = 32 * (LTC_EPI_WARPS + 1);  // warps 0-15: epilogue, warp 16: control
-constexpr int LTC_W_HALFS = 2 * 128 * 256;      // per (direction, rank): hi|lo x 128 rows x 256 k fp16 = 128 KB
 constexpr int LTC_HB_BUF = 16 * 1024;           // one h buffer: 16 K blocks x [k-unit 2][half 2][hi|lo][128 B] = 16 KB
 constexpr int LTC_HB_LBO = 256;                 // bytes between the two k-units (core matrices along K) of a K block
 constexpr int LTC_HB_SBO = 1024;                // bytes between the two 8-sequence halves (core matrices along N)
@@ -156,7 +155,7 @@ __device__ unsigned long long lstm_trace[4 * LTC_MAXG * 8];
 
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates (i,f,g,o) of (token, unit)
-               const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (LTC_W_HALFS per slice)
+               const uint4* __restrict__ w_img,     // [2][CS][hi|lo][32 k-units][128 rows] x 8 fp16 (2 x 128 x 256 fp16 = 128 KB per slice)
                const int32_t* __restrict__ tokens, const int32_t* __restrict__ lengths, int B, int T, int V,
                float* __restrict__ hfinal, int ns) {
   // ns = sequences of this cluster (<= 64), split into NG = ceil(ns/16) groups of <= 16 that share the W_hh slice in tensor
@@ -320,7 +319,7 @@ lstm_tc_kernel(const float4* __restrict__ xproj4,   // [2][V][H] float4 = gates 
           g_maxlen[gi] = max_len[g];
         }
     }
-    int my_len[LTC_GPS][2];
+    int my_len[LTC_GPS][2] = {};
     float c_state[LTC_GPS][2], h_state[LTC_GPS][2];
     float4 xn[LTC_GPS][2];
     const float4* xp_base = xproj4 + (size_t)dir * V * LTC_H + unit;

@@ -32,8 +32,6 @@ using namespace sm100;
 
 constexpr int TC_QM = 128;          // queries per tile (UMMA M)
 constexpr int TC_TILE_MAX = 128;    // DB rows per tile (UMMA N), multiple of 16
-constexpr int TC_STAGES = 4;
-constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 32 floats
 constexpr int TC_EPI_WARPS = 8;     // at most two per TMEM lane quadrant (they take alternate 16-column chunks of every tile)
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
 constexpr int TC_MAX_TILES_PER_CTA = 16;
@@ -983,7 +981,6 @@ retrieve_select_warp_kernel(const float* __restrict__ q, const float* __restrict
   };
 
   // candidate r lives in lane r
-  uint32_t my_key = 0u;
   int my_row = 0;
   double my_score = NINF;
   int n_cand = 0;
@@ -999,10 +996,7 @@ retrieve_select_warp_kernel(const float* __restrict__ q, const float* __restrict
       const unsigned who = __ballot_sync(0xffffffffu, bkey == m);
       const int winner = __ffs(who) - 1;
       const int wpos = __shfl_sync(0xffffffffu, bpos, winner);
-      if (lane == r) {
-        my_key = m;
-        my_row = row_of(wpos, m);
-      }
+      if (lane == r) my_row = row_of(wpos, m);
       if (lane == winner) {
         const int i = (wpos / KP - lane) >> 5;
         cur += 1ull << (6 * i);

@@ -31,6 +31,7 @@ using namespace sm100;
 constexpr int SGT_D = 128;
 constexpr int SGT_ROWS = 128;
 constexpr int SGT_HEADS = 4;
+static_assert(SGT_HEADS * 32 == 128, "head-major layout: 4 heads of 32 channels");
 constexpr int SGT_DH = 32;
 constexpr int SGT_CWARPS = 8;
 constexpr int SGT_CTHREADS = 32 * SGT_CWARPS;
@@ -295,7 +296,8 @@ superglue_tc_kernel(const float* __restrict__ blob, const __grid_constant__ t2p_
 
     const float inv_sqrt_dh = 1.f / sqrtf((float)SGT_DH);
     for (int layer = 0; layer < L; ++layer) {
-      const int tr0 = (layer == 4 || layer == 5) ? (layer - 4) * 16 : 64;
+      const int tr0 = (layer == 4 || layer == 5) ? (layer - 4) * 16 : 64;  // trace build only
+      (void)tr0;
       GTR(tr0 + 0);
       const float* bl = b_stream + (size_t)layer * SGT_BIAS_PER_LAYER;
       const float *bq = bl, *bk = bl + 128, *bv = bl + 256, *bm = bl + 384, *b0 = bl + 512, *b3 = bl + 768;

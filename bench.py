@@ -739,7 +739,7 @@ def main():
     ap.add_argument("--no-nccl", action="store_true", help="N > 1: skip the secondary timing with the NCCL exchange")
     ap.add_argument("--no-rows", action="store_true", help="skip the secondary measurements (DB build, cached fine stage)")
     ap.add_argument("--lstm-clusters", type=int, default=None, help="LSTM clusters per direction (default: 7 if depth == 1, 2 if depth < 8, else 1)")
-    ap.add_argument("--scan-ctas", type=int, default=None, help="top-k scan CTAs (default: one per SM if depth == 1, else 40)")
+    ap.add_argument("--scan-ctas", type=int, default=None, help="top-k scan CTAs (default: one per SM if depth == 1, else 24)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange: own peer-memory kernels or NCCL")
     ap.add_argument("--depth", type=int, default=20, help="batches in flight (one stream per slot)")
     ap.add_argument("--workload", default="coarse_online", choices=["coarse_online", "pipeline"],

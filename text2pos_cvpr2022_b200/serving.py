@@ -129,7 +129,7 @@ class OnlineRetrievalEngine:
         # streams several DB tiles against its resident query tile and the select reads fewer key lists: a fraction of the
         # SM-time per batch (T2P_RETRIEVE_MAX_CTAS)
         if scan_ctas is None:
-            scan_ctas = 0 if self.depth == 1 else 40
+            scan_ctas = 0 if self.depth == 1 else 24
         self.scan_ctas = max(0, min(255, int(scan_ctas)))
         self.topk_flags = self.scan_ctas << 8
         # slot 0 runs on the caller's current stream (query / enqueue_*); further slots own a stream each

@@ -148,3 +148,30 @@ def test_db_row_norm2_max_kernel():
     got = float(db_row_norm2_max(db.cuda()).cpu())
     want = float((db.double() ** 2).sum(1).max())
     assert abs(got - want) <= 1e-5 * want
+
+
+def test_scan_with_eight_epilogue_warps_in_a_fresh_process():
+    """T2P_SCAN_EPI=8 (two epilogue warps per TMEM lane quadrant, two key lists per query and CTA) is read once per process:
+    run the parity check for a single-tile, a multi-tile and a sharded-engine shape in a subprocess with it set."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, torch, oracle\n"
+        "from text2pos_cvpr2022_b200 import _lib, synthetic as syn\n"
+        "from text2pos_cvpr2022_b200.retrieval import retrieve_topk\n"
+        "for B, N, cap in ((64, 10000, 0), (64, 10000, 40), (512, 12500, 24), (7, 50, 0)):\n"
+        "    db = syn.synth_db_embeddings(N + 1, N, 256); q = syn.synth_query_embeddings(B + 2, B, 256)\n"
+        "    st = torch.zeros(2, dtype=torch.int32, device='cuda')\n"
+        "    idx, sc = retrieve_topk(q.cuda(), db.cuda(), 10, 5, flags=_lib.retrieve_max_ctas(cap), stats=st)\n"
+        "    ri, rs = oracle.retrieval.topk(db.numpy(), q.numpy(), 10)\n"
+        "    assert np.array_equal(idx.cpu().numpy(), ri + 5), (B, N, cap)\n"
+        "    assert np.allclose(sc.cpu().numpy(), rs, rtol=1e-12, atol=1e-15)\n"
+        "    assert sum(st.cpu().tolist()) == B\n"
+        "print('ok')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, T2P_SCAN_EPI="8", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr

@@ -5,7 +5,8 @@
 // thread and keeps, per query, a warp-distributed sorted list of its kp = k+6 best rows.
 // Stage 2 (retrieve_merge_kernel): one CTA per query merges the per-CTA lists, re-scores the kp finalists
 // in float64 (the reference ranks in float64, training/coarse.py:100-103,136) and orders them by
-// (score desc, index asc).  The kp > k margin makes the float32 pre-selection safe against rounding.
+// (score desc, index asc).  The float32 pre-selection is certified like the tensor path's: if the k-th exact score is not above
+// (kp-th float32 score + the float32 error bound), the CTA rescans the whole DB in float64.
 #include "kernels.h"
 #include "topk.cuh"
 
@@ -143,11 +144,17 @@ retrieve_partial_kernel(const float* __restrict__ q, const float* __restrict__ d
 __global__ void __launch_bounds__(128)
 retrieve_merge_kernel(const float* __restrict__ q, const float* __restrict__ db, int B, int N, int D, int G, int kp, int k,
                       int64_t idx_base, const float* __restrict__ part_s, const int32_t* __restrict__ part_i,
-                      double* __restrict__ out_s, int64_t* __restrict__ out_i) {
+                      const float* __restrict__ db_norm2_max, double* __restrict__ out_s, int64_t* __restrict__ out_i,
+                      int32_t* __restrict__ stats) {
   __shared__ float ws[4][RT_MAX_KP];
   __shared__ int32_t wi[4][RT_MAX_KP];
   __shared__ int32_t fin_i[RT_MAX_KP];
   __shared__ double fin_d[RT_MAX_KP];
+  __shared__ float sh_skp;      // float32 score of the kp-th finalist: no other row has a larger float32 score
+  __shared__ int sh_nvalid;     // finalists that are real rows (< kp: every row of the DB is a finalist)
+  __shared__ int sh_rescan;
+  __shared__ double rs_s[4][32];
+  __shared__ int64_t rs_i[4][32];
   const int qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float NEG_INF = __int_as_float(0xff800000);
@@ -174,6 +181,12 @@ retrieve_merge_kernel(const float* __restrict__ q, const float* __restrict__ db,
   if (warp == 0) {
     for (int w = 1; w < 4; ++w) top.offer(lane < kp && wi[w][lane] != 0x7fffffff, ws[w][lane], wi[w][lane]);
     fin_i[lane] = (lane < kp) ? top.i : 0x7fffffff;
+    const unsigned real = __ballot_sync(0xffffffffu, lane < kp && top.i != 0x7fffffff);
+    const float last = __shfl_sync(0xffffffffu, top.s, kp - 1);
+    if (lane == 0) {
+      sh_skp = last;
+      sh_nvalid = __popc(real);
+    }
   }
   __syncthreads();
   // float64 re-scoring of the finalists (lanes stride the channels; fixed-order tree reduction)
@@ -202,10 +215,69 @@ retrieve_merge_kernel(const float* __restrict__ q, const float* __restrict__ db,
       const bool gb = gd > my_d || (gd == my_d && (gi < my_i || (gi == my_i && g < lane)));
       rank += gb ? 1 : 0;
     }
-    if (have && rank < k) {
+    // certification (the float32 pre-selection is only a filter): every row that is not a finalist has a float32 score <= the
+    // kp-th finalist's, hence an exact score <= that + eps32 |q| max|d|; the ranking of the finalists stands only if the k-th
+    // exact score is strictly above this bound -- otherwise (scores near the top denser than float32 resolves, ties across
+    // the cut) the CTA rescans the DB in float64 below
+    double qq = 0.0;
+    for (int c = lane; c < D; c += 32) {
+      const double v = (double)__ldg(q + (size_t)qi * D + c);
+      qq = fma(v, v, qq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const unsigned kth = __ballot_sync(0xffffffffu, have && rank == k - 1 && my_i != 0x7fffffff);
+    const double tk = kth ? __shfl_sync(0xffffffffu, my_d, __ffs(kth) - 1) : NINF;
+    bool certified = true;
+    if (sh_nvalid >= kp) {  // some row may have been filtered out
+      const double eps32 = 1.5 * (double)(D + 8) * 5.9604644775390625e-08;  // float32 dot product: (D + O(1)) 2^-24, with margin
+      const double bound = (double)sh_skp + eps32 * sqrt(qq) * sqrt((double)__ldg(db_norm2_max) * (1.0 + 1e-5));
+      certified = tk > bound;
+    }
+    if (lane == 0) {
+      sh_rescan = certified ? 0 : 1;
+      if (stats) atomicAdd(stats + (certified ? 0 : 1), 1);
+    }
+    if (certified && have && rank < k) {
       const bool ok = my_i != 0x7fffffff;
       out_s[(size_t)qi * k + rank] = ok ? my_d : NINF;
       out_i[(size_t)qi * k + rank] = ok ? idx_base + (int64_t)my_i : (int64_t)-1;
+    }
+  }
+  __syncthreads();
+  if (sh_rescan == 0) return;
+  // exact float64 rescan of the whole DB for this query (rare)
+  {
+    const double NINF = __longlong_as_double(0xfff0000000000000LL);
+    const int64_t IMAX = 0x7fffffffffffffffLL;
+    WarpTopK<double, int64_t> top;
+    top.init(k, NINF, IMAX);
+    const float* qp = q + (size_t)qi * D;
+    for (int r0 = warp * 32; r0 < N; r0 += 128) {  // each warp: 32 consecutive rows per round, lane l keeps row r0 + l
+      double mine = NINF;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r = r0 + rr;
+        if (r < N) {  // warp-uniform
+          const float* dp = db + (size_t)r * D;
+          double acc = 0.0;
+          for (int c = lane; c < D; c += 32) acc = fma((double)__ldg(qp + c), (double)__ldg(dp + c), acc);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (lane == rr) mine = acc;
+        }
+      }
+      top.offer(r0 + lane < N, mine, (int64_t)(r0 + lane));
+    }
+    rs_s[warp][lane] = top.s;
+    rs_i[warp][lane] = top.i;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < 4; ++w) top.offer(lane < k && rs_i[w][lane] != IMAX, rs_s[w][lane], rs_i[w][lane]);
+      if (lane < k) {
+        const bool ok = top.i != IMAX;
+        out_s[(size_t)qi * k + lane] = ok ? top.s : NINF;
+        out_i[(size_t)qi * k + lane] = ok ? idx_base + top.i : (int64_t)-1;
+      }
     }
   }
 }
@@ -290,7 +362,7 @@ size_t t2p_retrieve_topk_workspace(int B, int N, int D, int k) {
   // generic path: G never exceeds the SM count of any sm_100 part we target (<= 160)
   const size_t G = 160;
   const size_t kp = std::min(RT_MAX_KP, k + 6);
-  size_t generic = align_up(G * B * kp * sizeof(float), 256) + align_up(G * B * kp * sizeof(int32_t), 256);
+  size_t generic = align_up(G * B * kp * sizeof(float), 256) + align_up(G * B * kp * sizeof(int32_t), 256) + 256 /* norm bound */;
   size_t tc = 0;
   for (int sms = 1; sms <= 160; ++sms) {  // the plan depends on the SM count / the CTA cap; size for the worst case
     const TcPlan p = tc_plan(B, N, D, k, sms);
@@ -300,19 +372,26 @@ size_t t2p_retrieve_topk_workspace(int B, int N, int D, int k) {
 }
 
 static int retrieve_generic(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
-                            double* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes, cudaStream_t s) {
+                            const float* d_db_norm2_max, double* d_out_scores, int64_t* d_out_idx, int32_t* d_stats, void* d_ws,
+                            size_t ws_bytes, cudaStream_t s) {
   T2P_REQUIRE(k >= 1 && k + 6 <= RT_MAX_KP, T2P_ERR_UNSUPPORTED, "retrieve_topk: k=%d outside [1,%d]", k, RT_MAX_KP - 6);
   const int sms = std::min(160, cached_sm_count());
   const RetrievePlan p = make_plan(B, N, D, k, sms);
   Arena a(d_ws, ws_bytes);
   float* part_s = a.take<float>((size_t)p.G * B * p.kp);
   int32_t* part_i = a.take<int32_t>((size_t)p.G * B * p.kp);
+  float* norm_slot = a.take<float>(1);
   T2P_REQUIRE(a.ok, T2P_ERR_WORKSPACE, "retrieve_topk: workspace %zu < %zu bytes", ws_bytes, a.used);
+  if (d_db_norm2_max == nullptr) {  // the certification bound needs max |d|: one extra pass over the DB
+    T2P_TRY(launch_row_norm2_max(d_db, N, D, norm_slot, s));
+    d_db_norm2_max = norm_slot;
+  }
   T2P_CUDA(cudaFuncSetAttribute(retrieve_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid(p.G, p.qtiles);
   retrieve_partial_kernel<<<grid, 16 * p.RG, p.smem, s>>>(d_q, d_db, B, N, D, p.rows_per_cta, p.RG, p.kp, part_s, part_i);
   T2P_LAUNCH_CHECK();
-  retrieve_merge_kernel<<<B, 128, 0, s>>>(d_q, d_db, B, N, D, p.G, p.kp, k, idx_base, part_s, part_i, d_out_scores, d_out_idx);
+  retrieve_merge_kernel<<<B, 128, 0, s>>>(d_q, d_db, B, N, D, p.G, p.kp, k, idx_base, part_s, part_i, d_db_norm2_max, d_out_scores,
+                                          d_out_idx, d_stats);
   T2P_LAUNCH_CHECK();
   return T2P_OK;
 }
@@ -333,7 +412,7 @@ int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int 
       return launch_retrieve_tc(p, d_q, d_db, B, N, D, k, idx_base, d_db_norm2_max, (flags & T2P_RETRIEVE_FORCE_RESCAN) ? 1 : 0,
                                 d_out_scores, d_out_idx, d_stats, d_ws, ws_bytes, s);
   }
-  return retrieve_generic(d_q, d_db, B, N, D, k, idx_base, d_out_scores, d_out_idx, d_ws, ws_bytes, s);
+  return retrieve_generic(d_q, d_db, B, N, D, k, idx_base, d_db_norm2_max, d_out_scores, d_out_idx, d_stats, d_ws, ws_bytes, s);
 }
 
 int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,

@@ -908,7 +908,7 @@ retrieve_select_kernel(const float* __restrict__ q, const float* __restrict__ db
 // (redux over the lanes' best heads); the first 16 candidates are re-scored in float64 (all row loads of 8 candidates in
 // flight), ranked with shuffles and CERTIFIED against the best remaining key exactly like retrieve_select_kernel; if that
 // fails the next 16 are added; a query that still cannot be certified is flagged for the CTA-per-query kernel (which also
-// owns the exact rescan).  8 queries per CTA: 64 queries occupy 8 SM slots for a few microseconds instead of 64 for 17.
+// owns the exact rescan).
 constexpr int SELW_WARPS = 2;   // queries per CTA: the kernel is instruction-bound per warp (~6k instructions per query), so the
                                 // warps are spread over many SMs (16 per CTA: 26 us for 64 queries on 4 SMs)
 constexpr int SELW_MAX_LPL = 10;  // lists per lane: nsrc <= 320

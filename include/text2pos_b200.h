@@ -74,15 +74,17 @@ int t2p_retrieve_topk(const float* d_q, const float* d_db, int B, int N, int D, 
  * computed on the tcgen05 tensor cores in TF32 (TMA-fed scan with an in-kernel top-k); the candidates are then
  * re-scored in float64 and the result is CERTIFIED against the TF32 error bound eps*|q|*max|d|, with an exact
  * float64 rescan of the DB for any query that cannot be certified -- the output is always the float64 ranking.
- * Other shapes take the exact-fp32 CUDA-core scan.
+ * Other shapes take the CUDA-core scan: float32 scores pre-select, float64 re-scores, and the same kind of certificate (float32
+ * error bound) decides whether a query needs the float64 rescan.
  *   d_db_norm2_max: device scalar = max squared row norm of the DB (t2p_db_row_norm2_max, computed once per DB);
  *                   NULL = compute it inside the call (one extra pass over the DB);
  *   flags:          T2P_RETRIEVE_*;
- *   d_stats:        optional device int32[2]: [0] += queries certified on the tensor path, [1] += queries rescanned. */
+ *   d_stats:        optional device int32[2]: [0] += queries certified from the fast scan, [1] += queries rescanned exactly. */
 #define T2P_RETRIEVE_FORCE_GENERIC 1 /* always use the CUDA-core scan */
 #define T2P_RETRIEVE_FORCE_RESCAN 2  /* tensor path, but treat every query as uncertified (tests the rescan) */
-#define T2P_RETRIEVE_MAX_CTAS(n) (((n) & 0xff) << 8) /* tensor path: at most n scan CTAs (0 = one per SM).  Fewer CTAs = less
-                                                        SM-time per batch at more latency: for servers with batches in flight */
+#define T2P_RETRIEVE_MAX_CTAS(n) (((n) & 0xff) << 8) /* tensor path: at most n scan CTAs in the whole launch, all query tiles
+                                                        together (0 = one per SM).  Fewer CTAs = less SM-time per batch at more
+                                                        latency: for servers with batches in flight */
 int t2p_retrieve_topk_ex(const float* d_q, const float* d_db, int B, int N, int D, int k, int64_t idx_base,
                          const float* d_db_norm2_max, int flags, double* d_out_scores, int64_t* d_out_idx,
                          int32_t* d_stats, void* d_ws, size_t ws_bytes, t2p_stream stream);
